@@ -1,0 +1,236 @@
+"""ctypes binding of include/gpsacq.h and a Python mirror of the reference's SearchTask().
+
+There is deliberately no numerical fallback here: if ``libgpsacq.so`` is missing or no CUDA
+device is usable, construction raises.  (The CPU oracle lives in ``oracle/`` and is test
+infrastructure only.)
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from pathlib import Path
+
+import numpy as np
+
+NUM_SATS = 32            # c/gps_offline.h:16
+FFT_LEN = 40000          # c/gps_offline.h:15
+SNR_THRESHOLD = 25.0     # c/search_offline.cpp:248
+
+_HERE = Path(__file__).resolve().parent
+
+
+class GpsAcqError(RuntimeError):
+    pass
+
+
+class _Cfg(C.Structure):
+    _fields_ = [("fc", C.c_double), ("fs", C.c_double), ("max_fo", C.c_double),
+                ("fft_len", C.c_int32), ("device", C.c_int32), ("max_blocks", C.c_int32),
+                ("reserved", C.c_int32)]
+
+
+class _Info(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in
+                ("abi_version", "fft_len", "n1", "n2", "window", "dmax", "n_doppler", "chunk_bytes",
+                 "max_blocks", "device", "sm_count", "cell_ctas", "cell_threads", "cell_smem_bytes")] + \
+               [("bytes_per_corr", C.c_int64)]
+
+
+PEAK_DTYPE = np.dtype([("snr", "<f4"), ("max_pwr", "<f4"), ("tot_pwr", "<f4"), ("lo_shift", "<i4"),
+                       ("ca_shift", "<i4"), ("sv", "<i4"), ("flags", "<i4"), ("reserved", "<i4")])
+CELL_DTYPE = np.dtype([("max_pwr", "<f4"), ("tot_pwr", "<f4"), ("max_idx", "<i4"), ("reserved", "<i4")])
+
+_LIB = None
+
+
+def lib_path() -> Path:
+    return Path(os.environ.get("GPSACQ_LIB", _HERE / "csrc" / "libgpsacq.so"))
+
+
+def load_library() -> C.CDLL:
+    """dlopen libgpsacq.so and declare every symbol of include/gpsacq.h."""
+    global _LIB
+    if _LIB is not None:
+        return _LIB
+    p = lib_path()
+    if not p.exists():
+        raise GpsAcqError(f"{p} not found: build it with __graft_entry__.build() "
+                          f"(nvcc, sm_100a); there is no CPU fallback")
+    lib = C.CDLL(str(p))
+    vp, i32p, u8p, f32p = C.c_void_p, C.POINTER(C.c_int32), C.POINTER(C.c_uint8), C.POINTER(C.c_float)
+    sigs = {
+        "gpsacq_create": (C.c_int, [C.POINTER(_Cfg), C.POINTER(vp)]),
+        "gpsacq_destroy": (None, [vp]),
+        "gpsacq_last_error": (C.c_char_p, [vp]),
+        "gpsacq_get_info": (C.c_int, [vp, C.POINTER(_Info)]),
+        "gpsacq_set_stream": (C.c_int, [vp, vp]),
+        "gpsacq_synchronize": (C.c_int, [vp]),
+        "gpsacq_search_blocks": (C.c_int, [vp, vp, C.c_size_t, vp, vp]),
+        "gpsacq_search_blocks_device": (C.c_int, [vp, vp, C.c_size_t, vp, vp]),
+        "gpsacq_stage_times": (C.c_int, [vp, f32p]),
+        "gpsacq_get_replica_time": (C.c_int, [vp, C.c_int, vp]),
+        "gpsacq_get_replica_spectrum": (C.c_int, [vp, C.c_int, vp]),
+        "gpsacq_get_block_spectrum": (C.c_int, [vp, C.c_size_t, vp]),
+        "gpsacq_get_cell_stats": (C.c_int, [vp, C.c_size_t, vp]),
+    }
+    for name, (res, args) in sigs.items():
+        fn = getattr(lib, name)          # AttributeError if the ABI lost a symbol
+        fn.restype, fn.argtypes = res, args
+    _LIB = lib
+    return lib
+
+
+ABI_SYMBOLS = ("gpsacq_create", "gpsacq_destroy", "gpsacq_last_error", "gpsacq_get_info",
+               "gpsacq_set_stream", "gpsacq_synchronize", "gpsacq_search_blocks",
+               "gpsacq_search_blocks_device", "gpsacq_stage_times", "gpsacq_get_replica_time",
+               "gpsacq_get_replica_spectrum", "gpsacq_get_block_spectrum", "gpsacq_get_cell_stats")
+
+
+class Acquisition:
+    """One engine instance = what SearchInit() sets up (c/search_offline.cpp:74-110).
+
+    fc, fs, max_fo are the reference's FC / FS / max_fo globals (c/gps_offline.h:23-25).
+    """
+
+    def __init__(self, fc: float, fs: float, max_fo: float = 5000.0, device: int = -1, max_blocks: int = 0):
+        self._lib = load_library()
+        self._h = C.c_void_p()
+        cfg = _Cfg(fc=fc, fs=fs, max_fo=max_fo, fft_len=0, device=device, max_blocks=max_blocks, reserved=0)
+        rc = self._lib.gpsacq_create(C.byref(cfg), C.byref(self._h))
+        if rc != 0:
+            msg = self._lib.gpsacq_last_error(None)
+            self._h = C.c_void_p()
+            raise GpsAcqError(f"gpsacq_create failed ({rc}): {msg.decode() if msg else '?'}")
+        info = _Info()
+        self._check(self._lib.gpsacq_get_info(self._h, C.byref(info)))
+        self.info = {n: getattr(info, n) for n, _ in _Info._fields_}
+        self.fc, self.fs, self.max_fo = fc, fs, max_fo
+
+    # -- plumbing -------------------------------------------------------------------
+    def _check(self, rc: int):
+        if rc != 0:
+            msg = self._lib.gpsacq_last_error(self._h)
+            raise GpsAcqError(f"libgpsacq error {rc}: {msg.decode() if msg else '?'}")
+
+    def close(self):
+        if getattr(self, "_h", None) and self._h.value:
+            self._lib.gpsacq_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    @property
+    def chunk_bytes(self) -> int:
+        return self.info["chunk_bytes"]
+
+    @property
+    def n_doppler(self) -> int:
+        return self.info["n_doppler"]
+
+    # -- the hot path ------------------------------------------------------------------
+    def search_blocks(self, bits, sv_of_block=None) -> np.ndarray:
+        """Sample()+Correlate() for every 5120-byte chunk of `bits` (host memory).
+
+        Chunk b is searched for PRN sv_of_block[b]+1 (default: b mod 32, the order
+        SearchTask() walks the file, c/search_offline.cpp:239-246).  Returns PEAK_DTYPE records.
+        """
+        buf = np.ascontiguousarray(np.frombuffer(bits, dtype=np.uint8) if not isinstance(bits, np.ndarray) else bits,
+                                   dtype=np.uint8)
+        cb = self.chunk_bytes
+        n_blocks = buf.size // cb
+        out = np.zeros(n_blocks, dtype=PEAK_DTYPE)
+        svp = None
+        if sv_of_block is not None:
+            sv = np.ascontiguousarray(sv_of_block, dtype=np.int32)
+            if sv.size != n_blocks:
+                raise ValueError("sv_of_block must have one entry per chunk")
+            svp = sv.ctypes.data
+        self._check(self._lib.gpsacq_search_blocks(self._h, buf.ctypes.data, n_blocks, svp, out.ctypes.data))
+        return out
+
+    def search_blocks_device(self, d_bits_ptr: int, n_blocks: int, d_sv_ptr: int | None, d_out_ptr: int):
+        """Asynchronous device-pointer variant (raw CUDA device addresses)."""
+        self._check(self._lib.gpsacq_search_blocks_device(self._h, d_bits_ptr, n_blocks, d_sv_ptr, d_out_ptr))
+
+    def set_stream(self, cuda_stream_ptr: int | None):
+        self._check(self._lib.gpsacq_set_stream(self._h, cuda_stream_ptr))
+
+    def synchronize(self):
+        self._check(self._lib.gpsacq_synchronize(self._h))
+
+    def stage_times(self) -> dict:
+        ms = (C.c_float * 4)()
+        self._check(self._lib.gpsacq_stage_times(self._h, ms))
+        return {"fwd_ms": ms[0], "cells_ms": ms[1], "best_ms": ms[2], "total_ms": ms[3]}
+
+    # -- parity probes -----------------------------------------------------------------
+    def replica_time(self, sv: int) -> np.ndarray:
+        out = np.empty(self.info["fft_len"], np.float32)
+        self._check(self._lib.gpsacq_get_replica_time(self._h, sv, out.ctypes.data))
+        return out
+
+    def replica_spectrum(self, sv: int) -> np.ndarray:
+        out = np.empty(self.info["fft_len"], np.complex64)
+        self._check(self._lib.gpsacq_get_replica_spectrum(self._h, sv, out.ctypes.data))
+        return out
+
+    def block_spectrum(self, block: int) -> np.ndarray:
+        out = np.empty(self.info["fft_len"], np.complex64)
+        self._check(self._lib.gpsacq_get_block_spectrum(self._h, block, out.ctypes.data))
+        return out
+
+    def cell_stats(self, block: int) -> np.ndarray:
+        out = np.zeros(self.n_doppler, CELL_DTYPE)
+        self._check(self._lib.gpsacq_get_cell_stats(self._h, block, out.ctypes.data))
+        return out
+
+
+# ---- SearchTask() report formatting (c/search_offline.cpp:264-287) -------------------------
+def format_run(run_count: int, peaks: np.ndarray) -> str:
+    """The six stdout lines SearchTask() prints for one run of 32 chunks."""
+    hits = [p for p in peaks if not (p["snr"] < SNR_THRESHOLD)]
+    out = []
+    out.append("%2d satellite: " % run_count + "".join("%5d " % p["sv"] for p in hits))
+    out.append("%2d SNR(>=25): " % run_count + "".join("%5.1f " % p["snr"] for p in hits))
+    out.append("%2d  lo_shift: " % run_count + "".join("%5d " % p["lo_shift"] for p in hits))
+    out.append("%2d  ca_shift: " % run_count + "".join("%5d " % p["ca_shift"] for p in hits))
+    out.append("".join("%2.0f " % p["snr"] for p in peaks))
+    out.append("")
+    return "\n".join(out) + "\n"
+
+
+def search_task_text(acq: Acquisition, filename: str, runs_per_batch: int = 16, max_runs: int | None = None) -> str:
+    """Python mirror of SearchTask(char*) (c/search_offline.cpp:219-292): same traversal of the
+    file (32 consecutive chunks per run, partial run discarded with "run out of file!"),
+    same report text.  Returns what the reference would print after the banner."""
+    try:
+        fp = open(filename, "rb")
+    except OSError:
+        return "can not open file!\n"
+    text = []
+    run_bytes = NUM_SATS * acq.chunk_bytes
+    run_count = 0
+    with fp:
+        while max_runs is None or run_count < max_runs:
+            want = runs_per_batch if max_runs is None else min(runs_per_batch, max_runs - run_count)
+            data = fp.read(want * run_bytes)
+            full = len(data) // run_bytes
+            if full:
+                peaks = acq.search_blocks(data[: full * run_bytes])
+                for r in range(full):
+                    text.append(format_run(run_count, peaks[r * NUM_SATS:(r + 1) * NUM_SATS]))
+                    run_count += 1
+            if full < want:
+                text.append("run out of file!\n")
+                break
+    return "".join(text)

@@ -1,0 +1,170 @@
+// ga_fft3.h -- the N = N1 * (RA*RB*RC) transform used by every kernel of the
+// acquisition engine, written per butterfly ("what does thread j do in pass X")
+// so that the same code runs inside the CUDA kernels and in the CPU replay under
+// tests/emu.
+//
+// Index algebra (DESIGN.md "FFT decomposition").  N2 = RA*RB*RC, N = N1*N2.
+// A length-N2 sequence lives in shared memory as a 3-D array P[a][b][c],
+// i = a*RB*RC + b*RC + c, at padded address a*SA + b*SB + c.  Three in-place
+// passes transform one axis each; thread-private radix butterflies, twiddles on
+// the outputs:
+//
+//   pass A  thread (b,c), j = b*RC+c :  t1[u,b,c] = tw^((N1*j + s)*u)      * sum_a w_RA^(au) P[a,b,c]
+//   pass B  thread (u,c)             :  t2[u,v,c] = tw^((N1*c + s)*RA*v)   * sum_b w_RB^(bv) t1[u,b,c]
+//   pass C  thread (u,v)             :  G [u,v,w] =                          sum_c w_RC^(cw) t2[u,v,c]
+//
+// with tw = exp(DIR*2*pi*i/N).  G[u,v,w] is output index tau = u + RA*v + RA*RB*w.
+// With s = 0 this is a plain N2-point DFT.  With s = 0..N1-1 and the final
+// factor exp(DIR*2*pi*i*s*w/(N1*RC)) it is the s-th term of the OUTPUT-PRUNED
+// N-point DFT  y[tau] = sum_s sum_i P[N1*i+s] w_N^((N1*i+s)*tau), tau < N2,
+// i.e. the reference's 40000-point backward FFT (c/search_offline.cpp:187)
+// evaluated only where Correlate() looks (i < FS/1000, :190).
+#pragma once
+#include "ga_radix.h"
+
+namespace ga {
+
+template <int N1_, int RA_, int RB_, int RC_>
+struct Geom {
+    static constexpr int N1 = N1_, RA = RA_, RB = RB_, RC = RC_;
+    static constexpr int N2 = RA * RB * RC, N = N1 * N2;
+    static constexpr int SB = RC | 1;        // odd row pitch: pass-C lanes (stride SB) hit distinct banks
+    static constexpr int SA = RB * SB;
+    static constexpr int SMEM_ELEMS = RA * SA;
+    static constexpr int NA = RB * RC, NB = RA * RC, NC = RA * RB;   // butterflies per pass
+    static constexpr int OUT_STRIDE = RA * RB;                        // tau step between a thread's outputs
+    GA_HD static int addr(int a, int b, int c) { return a * SA + b * SB + c; }
+};
+
+template <int DIR> GA_HD cf tw_load(const cf *tw, int idx)
+{
+    cf w = ldg(tw + idx);
+    return DIR > 0 ? w : cconj(w);
+}
+
+// ---- pass A tail: butterfly along a, twiddle, store -----------------------------
+template <class G, int DIR>
+GA_HD void passA_finish(cf (&p)[G::RA], int j, int s_tw, const cf *tw, cf *sm)
+{
+    Radix<G::RA, DIR>::run(p);
+    cf w[G::RA];
+    unit_powers<G::RA>(tw_load<DIR>(tw, G::N1 * j + s_tw), w);
+    const int b = j / G::RC, c = j - b * G::RC;
+    cf *dst = sm + G::addr(0, b, c);
+    dst[0] = p[0];
+    GA_UNROLL
+    for (int u = 1; u < G::RA; u++) dst[u * G::SA] = cmul(p[u], w[u]);
+}
+
+// ---- pass B: in place along b -----------------------------------------------------
+template <class G, int DIR>
+GA_HD void passB(int j2, int s_tw, const cf *tw, cf *sm)
+{
+    const int u = j2 / G::RC, c = j2 - u * G::RC;
+    cf *col = sm + G::addr(u, 0, c);
+    cf p[G::RB];
+    GA_UNROLL
+    for (int b = 0; b < G::RB; b++) p[b] = col[b * G::SB];
+    Radix<G::RB, DIR>::run(p);
+    cf w[G::RB];
+    unit_powers<G::RB>(tw_load<DIR>(tw, (G::N1 * c + s_tw) * G::RA), w);
+    col[0] = p[0];
+    GA_UNROLL
+    for (int v = 1; v < G::RB; v++) col[v * G::SB] = cmul(p[v], w[v]);
+}
+
+// ---- pass C: along c, results stay in registers ---------------------------------
+// returns tau0 = u + RA*v; p[w] is output tau0 + RA*RB*w
+template <class G, int DIR>
+GA_HD int passC(int j3, const cf *sm, cf (&p)[G::RC])
+{
+    const int u = j3 / G::RB, v = j3 - u * G::RB;
+    const cf *row = sm + G::addr(u, v, 0);
+    GA_UNROLL
+    for (int c = 0; c < G::RC; c++) p[c] = row[c];
+    Radix<G::RC, DIR>::run(p);
+    return u + G::RA * v;
+}
+
+// =====================================================================================
+// Cell = one (block, PRN, Doppler bin): shifted conj-multiply + pruned backward FFT.
+// =====================================================================================
+// For sub-sequence s of the product spectrum, prod[N1*i+s] = conj(X[N1*i+s]) *
+// C[(N1*i+s-dop) mod N] (c/search_offline.cpp:181-185).  With s-dop = N1*e + sp
+// (0 <= sp < N1) the code operand is the sp-th decimated sub-sequence of C rotated
+// by e.  Replica spectra are stored decimated and doubled (Cext[sp][t], t < 2*N2,
+// = C[N1*(t mod N2)+sp]) so the rotation is a plain offset.
+template <class G>
+GA_HD void cell_sub_offsets(int s, int dop, int &sp, int &eoff)
+{
+    const int v = s - dop;
+    int q = v / G::N1, r = v - q * G::N1;
+    if (r < 0) { r += G::N1; q -= 1; }       // floor division
+    sp = r;
+    eoff = q % G::N2; if (eoff < 0) eoff += G::N2;
+}
+
+// pass A of a cell: thread j of NA.  xs = conj(X) sub-sequence s (N2 values),
+// cs = Cext[sv][sp] + eoff.
+template <class G>
+GA_HD void cell_passA(int j, int s, const cf *xs, const cf *cs, const cf *tw, cf *sm)
+{
+    cf p[G::RA];
+    GA_UNROLL
+    for (int a = 0; a < G::RA; a++) {
+        const cf x = ldg(xs + a * G::NA + j), c = ldg(cs + a * G::NA + j);
+        p[a] = cmul(x, c);
+    }
+    passA_finish<G, +1>(p, j, s, tw, sm);
+}
+
+// pass C of a cell with accumulation of term s into the thread's outputs.
+// ks = ktab + s*RC, ktab[s*RC+w] = exp(+2*pi*i*s*w/(N1*RC)).
+template <class G, int NW>
+GA_HD void cell_passC_acc(int j3, const cf *sm, const cf *ks, cf (&acc)[NW])
+{
+    cf p[G::RC];
+    passC<G, +1>(j3, sm, p);
+    GA_UNROLL
+    for (int w = 0; w < NW; w++) cfma(acc[w], p[w], ks[w]);
+}
+
+// peak/sum over one thread's outputs (c/search_offline.cpp:190-194): power,
+// first-maximum (lowest tau wins ties), running sum.  wlen = search window.
+template <class G, int NW>
+GA_HD void cell_peak_thread(const cf (&acc)[NW], int tau0, int wlen, float &best, int &besti, float &sum)
+{
+    GA_UNROLL
+    for (int w = 0; w < NW; w++) {
+        const int tau = tau0 + G::OUT_STRIDE * w;
+        if (tau < wlen) {
+            const float pwr = fmaf(acc[w].x, acc[w].x, acc[w].y * acc[w].y);
+            if (pwr > best || (pwr == best && tau < besti)) { best = pwr; besti = tau; }
+            sum += pwr;
+        }
+    }
+}
+
+// =====================================================================================
+// Forward transform with decimated output:  X[N1*q+s], q < N2, for one s.
+//   X[N1*q+s] = sum_{n2<N2} w_N2^(-n2*q) * [ w_N^(-n2*s) * sum_{n1<N1} x[N2*n1+n2] w_N1^(-n1*s) ]
+// The bracket is the pass-A input; the outer sum is the plain (s_tw = 0) N2-point
+// forward transform.  Used for the sample blocks (Sample(), c/search_offline.cpp:161)
+// and the replicas (SearchInit(), :105).
+// =====================================================================================
+// src(n) returns time sample n as cf.  k1s = k1tab + s*N1, k1tab[s*N1+n1] = exp(-2*pi*i*n1*s/N1).
+template <class G, class Src>
+GA_HD void fwd_passA(int j, int s, const Src &src, const cf *k1s, const cf *tw, cf *sm)
+{
+    cf p[G::RA];
+    GA_UNROLL
+    for (int a = 0; a < G::RA; a++) {
+        const int n2 = a * G::NA + j;
+        cf z = src(n2);                                   // n1 = 0 term, K1 = 1
+        for (int n1 = 1; n1 < G::N1; n1++) cfma(z, src(G::N2 * n1 + n2), k1s[n1]);
+        p[a] = (s == 0) ? z : cmul(z, tw_load<-1>(tw, n2 * s));
+    }
+    passA_finish<G, -1>(p, j, 0, tw, sm);
+}
+
+}  // namespace ga

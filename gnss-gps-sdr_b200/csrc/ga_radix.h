@@ -1,0 +1,171 @@
+// ga_radix.h -- register-resident radix-R DFT butterflies (R = 2,4,5 primitives,
+// composites by Good-Thomas prime-factor mapping (no internal twiddles) or
+// Cooley-Tukey with compile-time twiddles).  DIR = +1: exp(+2*pi*i*nk/R)
+// (backward, what Correlate()'s rev_plan computes, c/search_offline.cpp:79,187);
+// DIR = -1: forward (fwd_plan, :78,:105,:161).
+//
+// All index maps are compile-time; with full unrolling every x[] element is a
+// register and the maps cost nothing.
+#pragma once
+#include "ga_common.h"
+#include <type_traits>
+
+namespace ga {
+
+// ---- compile-time trigonometry (so composite twiddles are immediates) --------
+constexpr double cx_pi = 3.14159265358979323846264338327950288;
+constexpr double cx_sin_series(double x)
+{   // |x| <= pi/2 after reduction; 15 terms are far below double epsilon
+    double term = x, sum = x, x2 = x * x;
+    for (int k = 1; k < 16; k++) { term *= -x2 / ((2.0 * k) * (2.0 * k + 1.0)); sum += term; }
+    return sum;
+}
+// sin(2*pi*p/q), cos(2*pi*p/q) for integers, exact symmetries first
+constexpr double cx_sin2pi(int p, int q)
+{
+    p %= q; if (p < 0) p += q;
+    if (2 * p > q) return -cx_sin2pi(q - p, q);            // second half-turn
+    if (4 * p > q) return cx_sin2pi(q - 2 * p, 2 * q);     // sin(pi - x) = sin x
+    return cx_sin_series(2.0 * cx_pi * p / q);
+}
+constexpr double cx_cos2pi(int p, int q) { return cx_sin2pi(4 * p + q, 4 * q); }  // cos x = sin(x + pi/2)
+
+constexpr int cx_inv_mod(int a, int m)
+{
+    a %= m;
+    for (int x = 1; x < m; x++) if ((a * x) % m == 1) return x;
+    return 1;
+}
+
+// ---- primitives --------------------------------------------------------------
+template <int R, int DIR> struct Radix;
+
+template <int DIR> struct Radix<1, DIR> { static GA_HD void run(cf (&)[1]) {} };
+
+template <int DIR> struct Radix<2, DIR> {
+    static GA_HD void run(cf (&x)[2])
+    {
+        cf a = x[0], b = x[1];
+        x[0] = cadd(a, b); x[1] = csub(a, b);
+    }
+};
+
+template <int DIR> struct Radix<4, DIR> {
+    static GA_HD void run(cf (&x)[4])
+    {
+        cf s0 = cadd(x[0], x[2]), d0 = csub(x[0], x[2]);
+        cf s1 = cadd(x[1], x[3]), d1 = cmul_i<DIR>(csub(x[1], x[3]));
+        x[0] = cadd(s0, s1); x[1] = cadd(d0, d1);
+        x[2] = csub(s0, s1); x[3] = csub(d0, d1);
+    }
+};
+
+template <int DIR> struct Radix<5, DIR> {
+    static GA_HD void run(cf (&x)[5])
+    {
+        constexpr float c1 = (float)cx_cos2pi(1, 5), c2 = (float)cx_cos2pi(2, 5);
+        constexpr float s1 = (float)(DIR * cx_sin2pi(1, 5)), s2 = (float)(DIR * cx_sin2pi(2, 5));
+        cf t1 = cadd(x[1], x[4]), t3 = csub(x[1], x[4]);
+        cf t2 = cadd(x[2], x[3]), t4 = csub(x[2], x[3]);
+        cf b1 = mk(fmaf(c2, t2.x, fmaf(c1, t1.x, x[0].x)), fmaf(c2, t2.y, fmaf(c1, t1.y, x[0].y)));
+        cf b2 = mk(fmaf(c1, t2.x, fmaf(c2, t1.x, x[0].x)), fmaf(c1, t2.y, fmaf(c2, t1.y, x[0].y)));
+        cf d1 = mk(fmaf(s2, t4.x, s1 * t3.x), fmaf(s2, t4.y, s1 * t3.y));
+        cf d2 = mk(fmaf(-s1, t4.x, s2 * t3.x), fmaf(-s1, t4.y, s2 * t3.y));
+        x[0] = cadd(x[0], cadd(t1, t2));
+        x[1] = mk(b1.x - d1.y, b1.y + d1.x);   // b1 + i*d1
+        x[4] = mk(b1.x + d1.y, b1.y - d1.x);
+        x[2] = mk(b2.x - d2.y, b2.y + d2.x);
+        x[3] = mk(b2.x + d2.y, b2.y - d2.x);
+    }
+};
+
+// ---- Good-Thomas: R = R1*R2, gcd(R1,R2) = 1, no twiddles ----------------------
+template <int R1, int R2, int DIR> struct PFA {
+    static constexpr int R = R1 * R2;
+    static GA_HD void run(cf (&x)[R1 * R2])
+    {
+        constexpr int A = R2 * cx_inv_mod(R2, R1);   // k = (A*k1 + B*k2) mod R
+        constexpr int B = R1 * cx_inv_mod(R1, R2);
+        cf t[R2][R1];
+        GA_UNROLL
+        for (int n2 = 0; n2 < R2; n2++) {
+            cf col[R1];
+            GA_UNROLL
+            for (int n1 = 0; n1 < R1; n1++) col[n1] = x[(R2 * n1 + R1 * n2) % R];
+            Radix<R1, DIR>::run(col);
+            GA_UNROLL
+            for (int k1 = 0; k1 < R1; k1++) t[n2][k1] = col[k1];
+        }
+        GA_UNROLL
+        for (int k1 = 0; k1 < R1; k1++) {
+            cf row[R2];
+            GA_UNROLL
+            for (int n2 = 0; n2 < R2; n2++) row[n2] = t[n2][k1];
+            Radix<R2, DIR>::run(row);
+            GA_UNROLL
+            for (int k2 = 0; k2 < R2; k2++) x[(A * k1 + B * k2) % R] = row[k2];
+        }
+    }
+};
+
+// ---- Cooley-Tukey: R = R1*R2 with compile-time twiddles -----------------------
+// compile-time loop: the body receives std::integral_constant<int, I>, so that
+// twiddles can be formed as constexpr immediates
+template <int I, int NITER, class F> GA_HD void static_for(F &&f)
+{
+    if constexpr (I < NITER) { f(std::integral_constant<int, I>{}); static_for<I + 1, NITER>(f); }
+}
+
+template <int R1, int R2, int DIR> struct CT {
+    static constexpr int R = R1 * R2;
+    static GA_HD void run(cf (&x)[R1 * R2])
+    {
+        cf t[R2][R1];
+        static_for<0, R2>([&](auto n2c) {
+            constexpr int n2 = decltype(n2c)::value;
+            cf col[R1];
+            GA_UNROLL
+            for (int n1 = 0; n1 < R1; n1++) col[n1] = x[R2 * n1 + n2];
+            Radix<R1, DIR>::run(col);
+            static_for<0, R1>([&](auto k1c) {
+                constexpr int k1 = decltype(k1c)::value;
+                if constexpr (n2 * k1 != 0) {
+                    constexpr float wr = (float)cx_cos2pi(n2 * k1, R);
+                    constexpr float wi = (float)(DIR * cx_sin2pi(n2 * k1, R));
+                    col[k1] = cmul(col[k1], mk(wr, wi));
+                }
+                t[n2][k1] = col[k1];
+            });
+        });
+        GA_UNROLL
+        for (int k1 = 0; k1 < R1; k1++) {
+            cf row[R2];
+            GA_UNROLL
+            for (int n2 = 0; n2 < R2; n2++) row[n2] = t[n2][k1];
+            Radix<R2, DIR>::run(row);
+            GA_UNROLL
+            for (int k2 = 0; k2 < R2; k2++) x[k1 + R1 * k2] = row[k2];
+        }
+    }
+};
+
+template <int DIR> struct Radix<8, DIR>  { static GA_HD void run(cf (&x)[8])  { CT<2, 4, DIR>::run(x); } };
+template <int DIR> struct Radix<10, DIR> { static GA_HD void run(cf (&x)[10]) { PFA<2, 5, DIR>::run(x); } };
+template <int DIR> struct Radix<16, DIR> { static GA_HD void run(cf (&x)[16]) { CT<4, 4, DIR>::run(x); } };
+template <int DIR> struct Radix<20, DIR> { static GA_HD void run(cf (&x)[20]) { PFA<4, 5, DIR>::run(x); } };
+template <int DIR> struct Radix<25, DIR> { static GA_HD void run(cf (&x)[25]) { CT<5, 5, DIR>::run(x); } };
+
+// powers of a unit complex number: w[k] = base^k, k < R, by a balanced product
+// tree (depth ~log2 R, so rounding stays at a few ulp).  w[0] is 1.
+template <int R> GA_HD void unit_powers(cf base, cf (&w)[R])
+{
+    w[0] = mk(1.0f, 0.0f);
+    if (R > 1) w[1] = base;
+    GA_UNROLL
+    for (int k = 2; k < R; k++) {
+        const int h = k / 2;
+        w[k] = (k & 1) ? cmul(w[h], w[h + 1]) : csqr(w[h]);
+    }
+}
+
+}  // namespace ga

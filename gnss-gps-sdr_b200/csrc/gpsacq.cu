@@ -1,0 +1,471 @@
+// gpsacq.cu -- C ABI (include/gpsacq.h) of the B200 GPS L1 C/A acquisition engine.
+//
+// Owns all device state (the reference keeps the same things in file statics,
+// c/search_offline.cpp:55-64): twiddle table, LO table, code-NCO tables, the 32
+// replica spectra, and per-batch workspaces.  No CPU compute path exists here: if
+// CUDA is unavailable gpsacq_create() fails.
+#include <cuda_runtime.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <math.h>
+#include <vector>
+#include <string>
+#include <algorithm>
+
+#include "../../include/gpsacq.h"
+#include "ga_kernels.cuh"
+#include "ga_tables.h"
+
+using namespace ga;
+
+static_assert(sizeof(gpsacq_peak) == sizeof(Peak) && sizeof(gpsacq_peak) == 32, "peak record layout");
+static_assert(sizeof(gpsacq_cell) == sizeof(CellStat) && sizeof(gpsacq_cell) == 16, "cell record layout");
+
+// ---- geometries: N = 40000 = N1 * (RA*RB*RC), N2 >= W --------------------------------
+typedef Geom<10, 20, 20, 10> G4000;    // W <= 4000   (FS <= 4 MHz, e.g. rtl-sdr 2.8 MHz)
+typedef Geom<5, 20, 20, 20> G8000;     // W <= 8000   (FS <= 8 MHz, e.g. 5.456 MHz)
+typedef Geom<4, 25, 20, 20> G10000;    // W <= 10000  (FS <= 10 MHz, e.g. 8.184 MHz, 10 MHz)
+enum { GID_4000 = 0, GID_8000 = 1, GID_10000 = 2 };
+
+#define CELL_T_4000 200
+#define CELL_T_8000 200
+#define CELL_T_10000 250
+#define FWD_T 256
+
+static const double kCPS = 1.023e6;    // chip rate, c/gps_offline.h:30
+
+// PRN -> G2 taps (c/search_offline.cpp:20-53; IS-GPS-200 Table 3-Ia), index = PRN-1
+static const unsigned char kTaps[32][2] = {
+    {2, 6}, {3, 7}, {4, 8}, {5, 9}, {1, 9}, {2, 10}, {1, 8}, {2, 9}, {3, 10}, {2, 3},
+    {3, 4}, {5, 6}, {6, 7}, {7, 8}, {8, 9}, {9, 10}, {1, 4}, {2, 5}, {3, 6}, {4, 7},
+    {5, 8}, {6, 9}, {1, 3}, {4, 6}, {5, 7}, {6, 8}, {7, 9}, {8, 10}, {1, 6}, {2, 7},
+    {3, 8}, {4, 9},
+};
+
+static thread_local std::string g_create_error;
+
+struct gpsacq {
+    gpsacq_cfg cfg;
+    int gid, n, n1, n2, w, dmax, ndop, chunk_bytes, chunk_samples, cap, device, sm_count;
+    int cell_ctas, cell_threads, cell_smem, cell_nw;
+    cudaStream_t own_stream, stream;
+    cudaEvent_t ev[4];
+    bool have_batch;
+    size_t last_blocks;
+    // device
+    cf *d_tw;
+    unsigned char *d_lo;
+    unsigned short *d_chip_idx;
+    float *d_blend_a, *d_blend_b, *d_repl_time;
+    cf *d_cext, *d_xd, *d_nat;
+    unsigned char *d_bits;
+    int *d_sv;
+    CellStat *d_cells;
+    Peak *d_peaks;
+    // pinned host staging
+    unsigned char *h_bits;
+    int *h_sv;
+    Peak *h_peaks;
+    std::string err;
+};
+
+#define CUDA_TRY(h, expr)                                                                          \
+    do {                                                                                           \
+        cudaError_t e_ = (expr);                                                                   \
+        if (e_ != cudaSuccess) {                                                                   \
+            char b_[512];                                                                          \
+            snprintf(b_, sizeof b_, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e_), __FILE__, __LINE__); \
+            (h)->err = b_;                                                                         \
+            return GPSACQ_ECUDA;                                                                   \
+        }                                                                                          \
+    } while (0)
+
+// ---- kernel dispatch ------------------------------------------------------------------
+template <class G, int T, int NW, int GID>
+static int launch_cells_t(gpsacq *h, size_t n_blocks, const int *d_sv)
+{
+    const int n_cells = (int)(n_blocks * (size_t)h->ndop);
+    const int grid = std::min(n_cells, h->cell_ctas);
+    cell_kernel<G, T, NW, 2, GID><<<grid, T, h->cell_smem, h->stream>>>(
+        h->d_xd, h->d_cext, d_sv, h->d_tw, n_cells, h->ndop, h->dmax, h->w, h->d_cells);
+    CUDA_TRY(h, cudaGetLastError());
+    return 0;
+}
+
+template <class G, int T, int NW, int GID>
+static int setup_cells_t(gpsacq *h)
+{
+    auto kern = cell_kernel<G, T, NW, 2, GID>;
+    h->cell_smem = (int)(G::SMEM_ELEMS * sizeof(cf));
+    h->cell_threads = T;
+    h->cell_nw = NW;
+    CUDA_TRY(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, h->cell_smem));
+    // ask for a shared-memory carveout that fits two CTAs (the rest stays L1 for the operand loads)
+    const int want = 2 * (h->cell_smem + 2048);
+    int pct = (int)((want * 100LL + 228 * 1024 - 1) / (228 * 1024));
+    if (pct > 100) pct = 100;
+    CUDA_TRY(h, cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, pct));
+    int per_sm = 0;
+    CUDA_TRY(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, T, h->cell_smem));
+    if (per_sm < 1) { h->err = "cell kernel does not fit on an SM"; return GPSACQ_ECUDA; }
+    h->cell_ctas = per_sm * h->sm_count;
+    return 0;
+}
+
+template <class G, int MODE, int GID>
+static int launch_fwd_t(gpsacq *h, size_t n_items, const unsigned char *d_bits, cf *out)
+{
+    auto kern = fwd_kernel<G, FWD_T, MODE, GID>;
+    const int smem = (int)(G::SMEM_ELEMS * sizeof(cf));
+    CUDA_TRY(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    kern<<<(unsigned)(n_items * G::N1), FWD_T, smem, h->stream>>>(d_bits, h->chunk_bytes, h->d_lo, h->d_repl_time,
+                                                                  h->d_tw, out);
+    CUDA_TRY(h, cudaGetLastError());
+    return 0;
+}
+
+static int setup_cells(gpsacq *h)
+{
+    switch (h->gid) {
+    case GID_4000:
+        return h->w <= 7 * G4000::OUT_STRIDE ? setup_cells_t<G4000, CELL_T_4000, 7, GID_4000>(h)
+                                             : setup_cells_t<G4000, CELL_T_4000, 10, GID_4000>(h);
+    case GID_8000:
+        return h->w <= 14 * G8000::OUT_STRIDE ? setup_cells_t<G8000, CELL_T_8000, 14, GID_8000>(h)
+                                              : setup_cells_t<G8000, CELL_T_8000, 20, GID_8000>(h);
+    default:
+        return h->w <= 17 * G10000::OUT_STRIDE ? setup_cells_t<G10000, CELL_T_10000, 17, GID_10000>(h)
+                                               : setup_cells_t<G10000, CELL_T_10000, 20, GID_10000>(h);
+    }
+}
+
+static int launch_cells(gpsacq *h, size_t n_blocks, const int *d_sv)
+{
+    switch (h->gid) {
+    case GID_4000:
+        return h->cell_nw == 7 ? launch_cells_t<G4000, CELL_T_4000, 7, GID_4000>(h, n_blocks, d_sv)
+                               : launch_cells_t<G4000, CELL_T_4000, 10, GID_4000>(h, n_blocks, d_sv);
+    case GID_8000:
+        return h->cell_nw == 14 ? launch_cells_t<G8000, CELL_T_8000, 14, GID_8000>(h, n_blocks, d_sv)
+                                : launch_cells_t<G8000, CELL_T_8000, 20, GID_8000>(h, n_blocks, d_sv);
+    default:
+        return h->cell_nw == 17 ? launch_cells_t<G10000, CELL_T_10000, 17, GID_10000>(h, n_blocks, d_sv)
+                                : launch_cells_t<G10000, CELL_T_10000, 20, GID_10000>(h, n_blocks, d_sv);
+    }
+}
+
+static int launch_fwd(gpsacq *h, int mode, size_t n_items, const unsigned char *d_bits, cf *out)
+{
+    switch (h->gid) {
+    case GID_4000:
+        return mode == 0 ? launch_fwd_t<G4000, 0, GID_4000>(h, n_items, d_bits, out) : launch_fwd_t<G4000, 1, GID_4000>(h, n_items, d_bits, out);
+    case GID_8000:
+        return mode == 0 ? launch_fwd_t<G8000, 0, GID_8000>(h, n_items, d_bits, out) : launch_fwd_t<G8000, 1, GID_8000>(h, n_items, d_bits, out);
+    default:
+        return mode == 0 ? launch_fwd_t<G10000, 0, GID_10000>(h, n_items, d_bits, out) : launch_fwd_t<G10000, 1, GID_10000>(h, n_items, d_bits, out);
+    }
+}
+
+template <class G, int GID> static int upload_const_t(gpsacq *h)
+{
+    std::vector<cf> kt = make_ktab<G>(), k1 = make_k1tab<G>();
+    CUDA_TRY(h, cudaMemcpyToSymbol(c_ktab, kt.data(), kt.size() * sizeof(cf), (size_t)GID * KTAB_MAX * sizeof(cf)));
+    CUDA_TRY(h, cudaMemcpyToSymbol(c_k1tab, k1.data(), k1.size() * sizeof(cf), (size_t)GID * K1TAB_MAX * sizeof(cf)));
+    return 0;
+}
+
+// ---- host-side sequential NCOs (must follow the reference's float recurrences) --------
+// Code NCO, SearchInit() c/search_offline.cpp:76,84-99.  For sample i: chip index before
+// the update, and the blend weights (1,0) or ((float)(1.0-ca_phase), ca_phase) on a
+// chip-edge crossing.
+static void build_code_nco(double fs, int n, std::vector<unsigned short> &idx, std::vector<float> &a, std::vector<float> &b)
+{
+    const float ca_rate = (float)(kCPS / fs);
+    float ca_phase = 0;
+    int chip = 0;
+    idx.resize(n); a.resize(n); b.resize(n);
+    for (int i = 0; i < n; i++) {
+        idx[i] = (unsigned short)chip;
+        ca_phase += ca_rate;
+        if (ca_phase >= 1.0) {
+            ca_phase -= 1.0;
+            chip = chip + 1 == 1023 ? 0 : chip + 1;
+            a[i] = (float)(1.0 - (double)ca_phase);
+            b[i] = ca_phase;
+        } else {
+            a[i] = 1.0f; b[i] = 0.0f;
+        }
+    }
+}
+
+// LO NCO, Sample() c/search_offline.cpp:124-127,131,152-156: per-sample phase index
+// int(lo_phase), packed as lo_cos bit | lo_sin bit << 1.
+static void build_lo_table(double fc, double fs, int n, std::vector<unsigned char> &lo)
+{
+    static const int lo_sin[4] = {1, 1, 0, 0}, lo_cos[4] = {0, 1, 1, 0};
+    const float lo_rate = (float)(4 * fc / fs);
+    float lo_phase = 0;
+    lo.resize(n);
+    for (int i = 0; i < n; i++) {
+        const int k = (int)lo_phase;
+        lo[i] = (unsigned char)(lo_cos[k & 3] | (lo_sin[k & 3] << 1));
+        lo_phase += lo_rate;
+        if (lo_phase >= 4) lo_phase -= 4;
+    }
+}
+
+static void free_all(gpsacq *h)
+{
+    if (!h) return;
+    cudaFree(h->d_tw); cudaFree(h->d_lo); cudaFree(h->d_chip_idx); cudaFree(h->d_blend_a); cudaFree(h->d_blend_b);
+    cudaFree(h->d_repl_time); cudaFree(h->d_cext); cudaFree(h->d_xd); cudaFree(h->d_nat); cudaFree(h->d_bits);
+    cudaFree(h->d_sv); cudaFree(h->d_cells); cudaFree(h->d_peaks);
+    cudaFreeHost(h->h_bits); cudaFreeHost(h->h_sv); cudaFreeHost(h->h_peaks);
+    for (int i = 0; i < 4; i++) if (h->ev[i]) cudaEventDestroy(h->ev[i]);
+    if (h->own_stream) cudaStreamDestroy(h->own_stream);
+}
+
+static int create_impl(gpsacq *h)
+{
+    const gpsacq_cfg &c = h->cfg;
+    if (!(c.fs > 0) || !(c.fc >= 0) || !(c.max_fo >= 0)) { h->err = "fc, fs, max_fo must be positive"; return GPSACQ_EINVAL; }
+    h->n = c.fft_len ? c.fft_len : GPSACQ_FFT_LEN;
+    if (h->n != GPSACQ_FFT_LEN) { h->err = "only fft_len = 40000 (FFT_LEN, c/gps_offline.h:15) is supported"; return GPSACQ_EINVAL; }
+    h->w = (int)ceil(c.fs / 1000.0);                          // for (i=0; i<FS/1000; i++)  (:190)
+    h->dmax = (int)(c.max_fo * (double)h->n / c.fs);          // C truncation, (:176)
+    h->ndop = 2 * h->dmax + 1;
+    h->chunk_samples = ((h->n + 4095) / 4096) * 4096;         // whole 512-byte packets (:129,:135-141)
+    h->chunk_bytes = h->chunk_samples / 8;
+    h->cap = c.max_blocks > 0 ? c.max_blocks : 512;
+    if (h->w <= G4000::N2) { h->gid = GID_4000; h->n1 = G4000::N1; h->n2 = G4000::N2; }
+    else if (h->w <= G8000::N2) { h->gid = GID_8000; h->n1 = G8000::N1; h->n2 = G8000::N2; }
+    else if (h->w <= G10000::N2) { h->gid = GID_10000; h->n1 = G10000::N1; h->n2 = G10000::N2; }
+    else { h->err = "sampling rates above 10 MHz (W > 10000) are not supported yet"; return GPSACQ_EINVAL; }
+    if (h->dmax >= h->n2) { h->err = "max_fo too large for this fft_len"; return GPSACQ_EINVAL; }
+
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0) {
+        h->err = std::string("no CUDA device available (") + cudaGetErrorString(e) + "); libgpsacq has no CPU fallback";
+        return GPSACQ_ECUDA;
+    }
+    if (c.device >= 0) { CUDA_TRY(h, cudaSetDevice(c.device)); }
+    CUDA_TRY(h, cudaGetDevice(&h->device));
+    cudaDeviceProp prop;
+    CUDA_TRY(h, cudaGetDeviceProperties(&prop, h->device));
+    if (prop.major < 10) { h->err = "libgpsacq is built for sm_100a (B200) only"; return GPSACQ_ECUDA; }
+    h->sm_count = prop.multiProcessorCount;
+
+    CUDA_TRY(h, cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking));
+    h->stream = h->own_stream;
+    for (int i = 0; i < 4; i++) CUDA_TRY(h, cudaEventCreate(&h->ev[i]));
+
+    const size_t n = (size_t)h->n, cap = (size_t)h->cap;
+    CUDA_TRY(h, cudaMalloc(&h->d_tw, n * sizeof(cf)));
+    CUDA_TRY(h, cudaMalloc(&h->d_lo, (size_t)h->chunk_samples));
+    CUDA_TRY(h, cudaMalloc(&h->d_chip_idx, n * sizeof(unsigned short)));
+    CUDA_TRY(h, cudaMalloc(&h->d_blend_a, n * sizeof(float)));
+    CUDA_TRY(h, cudaMalloc(&h->d_blend_b, n * sizeof(float)));
+    CUDA_TRY(h, cudaMalloc(&h->d_repl_time, 32 * n * sizeof(float)));
+    CUDA_TRY(h, cudaMalloc(&h->d_cext, 32 * 2 * n * sizeof(cf)));
+    CUDA_TRY(h, cudaMalloc(&h->d_xd, cap * n * sizeof(cf)));
+    CUDA_TRY(h, cudaMalloc(&h->d_nat, n * sizeof(cf)));
+    CUDA_TRY(h, cudaMalloc(&h->d_bits, cap * (size_t)h->chunk_bytes));
+    CUDA_TRY(h, cudaMalloc(&h->d_sv, cap * sizeof(int)));
+    CUDA_TRY(h, cudaMalloc(&h->d_cells, cap * (size_t)h->ndop * sizeof(CellStat)));
+    CUDA_TRY(h, cudaMalloc(&h->d_peaks, cap * sizeof(Peak)));
+    CUDA_TRY(h, cudaMallocHost(&h->h_bits, cap * (size_t)h->chunk_bytes));
+    CUDA_TRY(h, cudaMallocHost(&h->h_sv, cap * sizeof(int)));
+    CUDA_TRY(h, cudaMallocHost(&h->h_peaks, cap * sizeof(Peak)));
+
+    // constant tables
+    std::vector<cf> tw = make_tw(h->n);
+    CUDA_TRY(h, cudaMemcpy(h->d_tw, tw.data(), n * sizeof(cf), cudaMemcpyHostToDevice));
+    int rc = h->gid == GID_4000 ? upload_const_t<G4000, GID_4000>(h)
+           : h->gid == GID_8000 ? upload_const_t<G8000, GID_8000>(h) : upload_const_t<G10000, GID_10000>(h);
+    if (rc) return rc;
+    std::vector<unsigned char> lo;
+    build_lo_table(c.fc, c.fs, h->chunk_samples, lo);
+    CUDA_TRY(h, cudaMemcpy(h->d_lo, lo.data(), lo.size(), cudaMemcpyHostToDevice));
+    std::vector<unsigned short> ci; std::vector<float> ba, bb;
+    build_code_nco(c.fs, h->n, ci, ba, bb);
+    CUDA_TRY(h, cudaMemcpy(h->d_chip_idx, ci.data(), n * sizeof(unsigned short), cudaMemcpyHostToDevice));
+    CUDA_TRY(h, cudaMemcpy(h->d_blend_a, ba.data(), n * sizeof(float), cudaMemcpyHostToDevice));
+    CUDA_TRY(h, cudaMemcpy(h->d_blend_b, bb.data(), n * sizeof(float), cudaMemcpyHostToDevice));
+
+    rc = setup_cells(h);
+    if (rc) return rc;
+
+    // replicas: time domain, then forward FFT into the decimated + doubled layout
+    SatTaps taps;
+    for (int sv = 0; sv < 32; sv++) { taps.t0[sv] = kTaps[sv][0]; taps.t1[sv] = kTaps[sv][1]; }
+    replica_time_kernel<<<32, 256, 0, h->stream>>>(taps, h->d_chip_idx, h->d_blend_a, h->d_blend_b, h->n, h->d_repl_time);
+    CUDA_TRY(h, cudaGetLastError());
+    rc = launch_fwd(h, 1, 32, nullptr, h->d_cext);
+    if (rc) return rc;
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+// ---- ABI -------------------------------------------------------------------------------
+extern "C" {
+
+int gpsacq_create(const gpsacq_cfg *cfg, gpsacq_t **out)
+{
+    if (!cfg || !out) { g_create_error = "null argument"; return GPSACQ_EINVAL; }
+    *out = nullptr;
+    gpsacq *h = new (std::nothrow) gpsacq();
+    if (!h) { g_create_error = "out of host memory"; return GPSACQ_ENOMEM; }
+    h->cfg = *cfg;
+    int rc = create_impl(h);
+    if (rc) {
+        g_create_error = h->err;
+        free_all(h);
+        delete h;
+        return rc;
+    }
+    *out = h;
+    return GPSACQ_OK;
+}
+
+void gpsacq_destroy(gpsacq_t *h)
+{
+    if (!h) return;
+    cudaSetDevice(h->device);
+    cudaStreamSynchronize(h->stream);
+    free_all(h);
+    delete h;
+}
+
+const char *gpsacq_last_error(const gpsacq_t *h) { return h ? h->err.c_str() : g_create_error.c_str(); }
+
+int gpsacq_get_info(const gpsacq_t *h, gpsacq_info *info)
+{
+    if (!h || !info) return GPSACQ_EINVAL;
+    memset(info, 0, sizeof *info);
+    info->abi_version = GPSACQ_ABI_VERSION;
+    info->fft_len = h->n; info->n1 = h->n1; info->n2 = h->n2;
+    info->window = h->w; info->dmax = h->dmax; info->n_doppler = h->ndop;
+    info->chunk_bytes = h->chunk_bytes; info->max_blocks = h->cap;
+    info->device = h->device; info->sm_count = h->sm_count;
+    info->cell_ctas = h->cell_ctas; info->cell_threads = h->cell_threads; info->cell_smem_bytes = h->cell_smem;
+    info->bytes_per_corr = 2LL * h->n * 8 + 16;
+    return GPSACQ_OK;
+}
+
+int gpsacq_set_stream(gpsacq_t *h, void *cuda_stream)
+{
+    if (!h) return GPSACQ_EINVAL;
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    h->stream = cuda_stream ? (cudaStream_t)cuda_stream : h->own_stream;
+    return GPSACQ_OK;
+}
+
+int gpsacq_synchronize(gpsacq_t *h)
+{
+    if (!h) return GPSACQ_EINVAL;
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    return GPSACQ_OK;
+}
+
+int gpsacq_search_blocks_device(gpsacq_t *h, const uint8_t *d_bits, size_t n_blocks, const int32_t *d_sv, gpsacq_peak *d_out)
+{
+    if (!h || !d_bits || !d_out) return GPSACQ_EINVAL;
+    if (n_blocks == 0) return GPSACQ_OK;
+    if (n_blocks > (size_t)h->cap) { h->err = "n_blocks exceeds max_blocks"; return GPSACQ_EINVAL; }
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    CUDA_TRY(h, cudaEventRecord(h->ev[0], h->stream));
+    int rc = launch_fwd(h, 0, n_blocks, d_bits, h->d_xd);
+    if (rc) return rc;
+    CUDA_TRY(h, cudaEventRecord(h->ev[1], h->stream));
+    rc = launch_cells(h, n_blocks, d_sv);
+    if (rc) return rc;
+    CUDA_TRY(h, cudaEventRecord(h->ev[2], h->stream));
+    best_kernel<<<(unsigned)((n_blocks + 127) / 128), 128, 0, h->stream>>>(h->d_cells, d_sv, (int)n_blocks, h->ndop, h->dmax, h->w, (Peak *)d_out);
+    CUDA_TRY(h, cudaGetLastError());
+    CUDA_TRY(h, cudaEventRecord(h->ev[3], h->stream));
+    h->have_batch = true;
+    h->last_blocks = n_blocks;
+    return GPSACQ_OK;
+}
+
+int gpsacq_search_blocks(gpsacq_t *h, const uint8_t *bits, size_t n_blocks, const int32_t *sv_of_block, gpsacq_peak *out)
+{
+    if (!h || (!bits && n_blocks) || (!out && n_blocks)) return GPSACQ_EINVAL;
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    for (size_t done = 0; done < n_blocks;) {
+        const size_t nb = std::min((size_t)h->cap, n_blocks - done);
+        memcpy(h->h_bits, bits + done * (size_t)h->chunk_bytes, nb * (size_t)h->chunk_bytes);
+        for (size_t b = 0; b < nb; b++) {
+            const int sv = sv_of_block ? sv_of_block[done + b] : (int)((done + b) % GPSACQ_NUM_SATS);
+            if (sv < 0 || sv >= GPSACQ_NUM_SATS) { h->err = "sv_of_block entry out of range 0..31"; return GPSACQ_EINVAL; }
+            h->h_sv[b] = sv;
+        }
+        CUDA_TRY(h, cudaMemcpyAsync(h->d_bits, h->h_bits, nb * (size_t)h->chunk_bytes, cudaMemcpyHostToDevice, h->stream));
+        CUDA_TRY(h, cudaMemcpyAsync(h->d_sv, h->h_sv, nb * sizeof(int), cudaMemcpyHostToDevice, h->stream));
+        int rc = gpsacq_search_blocks_device(h, h->d_bits, nb, h->d_sv, (gpsacq_peak *)h->d_peaks);
+        if (rc) return rc;
+        CUDA_TRY(h, cudaMemcpyAsync(h->h_peaks, h->d_peaks, nb * sizeof(Peak), cudaMemcpyDeviceToHost, h->stream));
+        CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+        memcpy(out + done, h->h_peaks, nb * sizeof(Peak));
+        done += nb;
+    }
+    return GPSACQ_OK;
+}
+
+int gpsacq_stage_times(gpsacq_t *h, float ms[4])
+{
+    if (!h || !ms) return GPSACQ_EINVAL;
+    if (!h->have_batch) { h->err = "no batch processed yet"; return GPSACQ_ESTATE; }
+    CUDA_TRY(h, cudaEventSynchronize(h->ev[3]));
+    CUDA_TRY(h, cudaEventElapsedTime(&ms[0], h->ev[0], h->ev[1]));
+    CUDA_TRY(h, cudaEventElapsedTime(&ms[1], h->ev[1], h->ev[2]));
+    CUDA_TRY(h, cudaEventElapsedTime(&ms[2], h->ev[2], h->ev[3]));
+    CUDA_TRY(h, cudaEventElapsedTime(&ms[3], h->ev[0], h->ev[3]));
+    return GPSACQ_OK;
+}
+
+int gpsacq_get_replica_time(gpsacq_t *h, int sv, float *out)
+{
+    if (!h || !out || sv < 0 || sv >= 32) return GPSACQ_EINVAL;
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    CUDA_TRY(h, cudaMemcpy(out, h->d_repl_time + (size_t)sv * h->n, (size_t)h->n * sizeof(float), cudaMemcpyDeviceToHost));
+    return GPSACQ_OK;
+}
+
+static int read_natural(gpsacq *h, const cf *src, int mode, float *out)
+{
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    undecimate_kernel<<<(h->n + 255) / 256, 256, 0, h->stream>>>(src, h->n1, h->n2, mode, h->d_nat);
+    CUDA_TRY(h, cudaGetLastError());
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    CUDA_TRY(h, cudaMemcpy(out, h->d_nat, (size_t)h->n * sizeof(cf), cudaMemcpyDeviceToHost));
+    return GPSACQ_OK;
+}
+
+int gpsacq_get_replica_spectrum(gpsacq_t *h, int sv, float *out)
+{
+    if (!h || !out || sv < 0 || sv >= 32) return GPSACQ_EINVAL;
+    return read_natural(h, h->d_cext + (size_t)sv * 2 * h->n, 1, out);
+}
+
+int gpsacq_get_block_spectrum(gpsacq_t *h, size_t blk, float *out)
+{
+    if (!h || !out) return GPSACQ_EINVAL;
+    if (!h->have_batch || blk >= h->last_blocks) { h->err = "block index outside the last batch"; return GPSACQ_ESTATE; }
+    return read_natural(h, h->d_xd + blk * (size_t)h->n, 0, out);
+}
+
+int gpsacq_get_cell_stats(gpsacq_t *h, size_t blk, gpsacq_cell *out)
+{
+    if (!h || !out) return GPSACQ_EINVAL;
+    if (!h->have_batch || blk >= h->last_blocks) { h->err = "block index outside the last batch"; return GPSACQ_ESTATE; }
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    CUDA_TRY(h, cudaMemcpy(out, h->d_cells + blk * (size_t)h->ndop, (size_t)h->ndop * sizeof(CellStat), cudaMemcpyDeviceToHost));
+    return GPSACQ_OK;
+}
+
+}  // extern "C"

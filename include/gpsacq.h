@@ -1,0 +1,155 @@
+/*
+ * include/gpsacq.h -- C ABI of libgpsacq.so, the B200 (sm_100a) GPS L1 C/A
+ * acquisition engine.
+ *
+ * This is the drop-in boundary for the reference's offline search path
+ * (JiaoXianjun/GNSS-GPS-SDR, c/search_offline.cpp).  The reference exposes that
+ * path as five C++-linkage functions plus three caller-defined globals
+ * (c/gps_offline.h:23-25, :87-91):
+ *
+ *     extern double FC, FS, max_fo;
+ *     int  SearchInit();  void SearchFree();  void SearchTask(char *file);
+ *     void SearchEnable(int sv);  int SearchCode(int sv, int g1);
+ *
+ * and keeps all state in file statics (code[32][40000], fwd_buf, rev_buf, two
+ * FFTW plans; c/search_offline.cpp:55-64).  The host C++ in
+ * gnss-gps-sdr_b200/c/ re-implements those five symbols on top of the entry
+ * points below; nothing here uses C++ or torch types, so cgo / JNI / ctypes
+ * bindings work the same way (INTEGRATION.md shows them).
+ *
+ * What each entry point replaces:
+ *   gpsacq_create            SearchInit()  c/search_offline.cpp:74-110  (replica generation + 32 forward
+ *                                          FFTs; also reads FC/FS/max_fo like Sample()/Correlate() do,
+ *                                          :76,:127,:176,:190) -- but on the device, into HBM.
+ *   gpsacq_destroy           SearchFree()  :114-117
+ *   gpsacq_search_blocks     the body of SearchTask()'s satellite loop, :239-257:
+ *                            Sample() :121-165 (unpack, XOR mix, forward FFT) and
+ *                            Correlate() :169-201 (Doppler loop, shifted conj-multiply,
+ *                            backward FFT, |.|^2, peak/mean, best over Doppler) for a batch
+ *                            of 5120-byte chunks.  REF semantics: chunk b is searched for
+ *                            PRN (b mod 32)+1, or sv_of_block[b]+1 when given.
+ *   gpsacq_search_blocks_device   same with device-resident input/output (no copies).
+ *   gpsacq_get_*             test probes: read back what the reference holds in code[sv],
+ *                            fwd_buf and the per-Doppler (max_pwr, max_pwr_i, tot_pwr) locals.
+ *
+ * Error convention: every int function returns 0 on success, a negative
+ * GPSACQ_E* code otherwise; gpsacq_last_error() gives the text.  There is NO
+ * CPU fallback: without a usable CUDA device gpsacq_create() fails with
+ * GPSACQ_ECUDA.
+ *
+ * Threading: one host thread per handle at a time (the reference is not
+ * re-entrant at all).  Several handles (e.g. one per GPU) may be used
+ * concurrently from different threads.
+ */
+#ifndef GPSACQ_H
+#define GPSACQ_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GPSACQ_ABI_VERSION 1
+
+#define GPSACQ_OK        0
+#define GPSACQ_EINVAL   (-1)   /* bad argument / unsupported configuration        */
+#define GPSACQ_ECUDA    (-2)   /* CUDA runtime error or no device                 */
+#define GPSACQ_ENOMEM   (-3)   /* host or device allocation failed                */
+#define GPSACQ_ESTATE   (-4)   /* probe called before any batch was processed     */
+
+#define GPSACQ_NUM_SATS 32     /* NUM_SATS, c/gps_offline.h:16                     */
+#define GPSACQ_FFT_LEN  40000  /* FFT_LEN,  c/gps_offline.h:15                     */
+
+typedef struct gpsacq gpsacq_t;
+
+typedef struct gpsacq_cfg {
+    double  fc;          /* carrier at IF, Hz        (extern double FC,     c/gps_offline.h:23) */
+    double  fs;          /* sampling rate, Hz        (extern double FS,     :24)               */
+    double  max_fo;      /* Doppler search half-span (extern double max_fo, :25)               */
+    int32_t fft_len;     /* 0 = GPSACQ_FFT_LEN; only 40000 is supported                        */
+    int32_t device;      /* CUDA device ordinal; -1 = current device                           */
+    int32_t max_blocks;  /* batch capacity in chunks; 0 = 512 (16 runs of 32 PRNs)             */
+    int32_t reserved;
+} gpsacq_cfg;
+
+/* One record per searched chunk = what Correlate() returns plus its inputs to the
+ * snr division (c/search_offline.cpp:196-200). */
+typedef struct gpsacq_peak {
+    float   snr;         /* max over Doppler of max_pwr/(tot_pwr/W); 0 if none > 0 (:173,:198)  */
+    float   max_pwr;     /* of the winning Doppler bin                                         */
+    float   tot_pwr;     /* of the winning Doppler bin                                         */
+    int32_t lo_shift;    /* winning Doppler bin, -dmax..+dmax  (*max_snr_dop, :198)            */
+    int32_t ca_shift;    /* code phase in samples, 0..W-1      (*max_snr_i,   :198)            */
+    int32_t sv;          /* 0-based satellite index (PRN-1) this chunk was searched for        */
+    int32_t flags;       /* bit0: snr >= 25 (the SearchTask() detection rule, :248)            */
+    int32_t reserved;
+} gpsacq_peak;
+
+/* Per-(chunk, Doppler bin) statistics: Correlate()'s max_pwr, max_pwr_i, tot_pwr (:177-194). */
+typedef struct gpsacq_cell {
+    float   max_pwr;
+    float   tot_pwr;
+    int32_t max_idx;
+    int32_t reserved;
+} gpsacq_cell;
+
+typedef struct gpsacq_info {
+    int32_t abi_version;
+    int32_t fft_len;       /* N                                                   */
+    int32_t n1, n2;        /* N = n1*n2: n1 decimated sub-sequences of n2 points   */
+    int32_t window;        /* W = ceil(FS/1000) code phases searched (:190)        */
+    int32_t dmax;          /* Doppler bins -dmax..+dmax (:176)                     */
+    int32_t n_doppler;     /* 2*dmax+1                                             */
+    int32_t chunk_bytes;   /* bytes consumed per chunk (5120 for N=40000, :129-141)*/
+    int32_t max_blocks;    /* batch capacity                                       */
+    int32_t device;        /* CUDA ordinal in use                                  */
+    int32_t sm_count;
+    int32_t cell_ctas;     /* persistent CTAs of the cell kernel                   */
+    int32_t cell_threads;
+    int32_t cell_smem_bytes;
+    int64_t bytes_per_corr;/* algorithmic bytes per (PRN,Doppler) correlation: 2*N*8+16 */
+} gpsacq_info;
+
+/* Number of kernels this library launches for a batch (for bench.py's gpu_launches). */
+#define GPSACQ_LAUNCHES_PER_BATCH 3
+
+int  gpsacq_create(const gpsacq_cfg *cfg, gpsacq_t **out);
+void gpsacq_destroy(gpsacq_t *h);
+const char *gpsacq_last_error(const gpsacq_t *h);   /* h may be NULL: error of the last failed create */
+int  gpsacq_get_info(const gpsacq_t *h, gpsacq_info *info);
+
+/* Use an existing CUDA stream (cudaStream_t passed as void*) for all work of this
+ * handle; NULL restores the handle's own stream. */
+int  gpsacq_set_stream(gpsacq_t *h, void *cuda_stream);
+int  gpsacq_synchronize(gpsacq_t *h);
+
+/* Host-buffer search: packed_bits = n_blocks * chunk_bytes bytes of 1-bit samples,
+ * LSB first (c/search_offline.cpp:143-146).  sv_of_block may be NULL (REF rule:
+ * b mod 32).  out receives n_blocks records.  Any n_blocks; batches internally.
+ * Includes the host->device and device->host copies and a stream synchronise. */
+int  gpsacq_search_blocks(gpsacq_t *h, const uint8_t *packed_bits, size_t n_blocks,
+                          const int32_t *sv_of_block, gpsacq_peak *out);
+
+/* Device-buffer search, asynchronous on the handle's stream.  n_blocks <= max_blocks.
+ * d_sv_of_block may be NULL. */
+int  gpsacq_search_blocks_device(gpsacq_t *h, const uint8_t *d_packed_bits, size_t n_blocks,
+                                 const int32_t *d_sv_of_block, gpsacq_peak *d_out);
+
+/* Elapsed milliseconds of the stages of the most recent batch, measured with CUDA
+ * events on the launching stream: [0] unpack+mix+forward FFT kernel, [1] cell kernel
+ * (conj-multiply + backward FFT + peak), [2] best-over-Doppler kernel, [3] whole batch.
+ * Synchronises the stream. */
+int  gpsacq_stage_times(gpsacq_t *h, float ms[4]);
+
+/* ---- parity probes (copy device state to host; synchronise) -------------------- */
+int  gpsacq_get_replica_time(gpsacq_t *h, int sv, float *out /* fft_len floats */);
+int  gpsacq_get_replica_spectrum(gpsacq_t *h, int sv, float *out /* 2*fft_len: re,im of C[k] */);
+int  gpsacq_get_block_spectrum(gpsacq_t *h, size_t block_in_last_batch, float *out /* 2*fft_len: X[k] */);
+int  gpsacq_get_cell_stats(gpsacq_t *h, size_t block_in_last_batch, gpsacq_cell *out /* n_doppler */);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GPSACQ_H */

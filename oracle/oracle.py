@@ -1,0 +1,226 @@
+"""oracle/oracle.py -- TEST INFRASTRUCTURE ONLY.
+
+ctypes front-end of the CPU oracle:
+  * ``Oracle``      -- the C restatement (oracle/gpsacq_oracle.c -> oracle/liboracle.so)
+  * ``RefHarness``  -- the UNMODIFIED reference translation unit compiled against the
+                       fftw3.h stand-in (oracle/_ref/libref_harness.so; built only where
+                       /root/reference exists, prebuilt file travels to the GPU box)
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may
+import this module.  The product (gnss-gps-sdr_b200/, include/) never does.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+from pathlib import Path
+
+import numpy as np
+
+HERE = Path(__file__).resolve().parent
+PEAK_DTYPE = np.dtype([("snr", "<f4"), ("max_pwr", "<f4"), ("tot_pwr", "<f4"), ("lo_shift", "<i4"),
+                       ("ca_shift", "<i4"), ("sv", "<i4"), ("flags", "<i4"), ("reserved", "<i4")])
+TORCH_MKL = None
+
+
+def build(quiet: bool = True) -> None:
+    """make -C oracle (liboracle.so always; _ref/ only when /root/reference is present)."""
+    subprocess.run(["make", "-C", str(HERE)], check=True,
+                   stdout=subprocess.DEVNULL if quiet else None)
+
+
+def _lib() -> C.CDLL:
+    p = HERE / "liboracle.so"
+    if not p.exists():
+        build()
+    lib = C.CDLL(str(p))
+    vp = C.c_void_p
+    lib.oracle_create.restype = vp
+    lib.oracle_create.argtypes = [C.c_double, C.c_double, C.c_double, C.c_int, C.c_int]
+    lib.oracle_destroy.argtypes = [vp]
+    for f in ("oracle_num_doppler", "oracle_window", "oracle_chunk_bytes", "oracle_fft_len"):
+        getattr(lib, f).restype = C.c_int
+        getattr(lib, f).argtypes = [vp]
+    lib.oracle_code_spectrum.restype = vp
+    lib.oracle_code_spectrum.argtypes = [vp, C.c_int]
+    lib.oracle_sample.argtypes = [vp, vp, vp]
+    lib.oracle_cells.argtypes = [vp, vp, C.c_int, vp, vp, vp]
+    lib.oracle_search_blocks.restype = C.c_int
+    lib.oracle_search_blocks.argtypes = [vp, vp, C.c_int, vp, vp]
+    lib.oracle_cacode_chips.argtypes = [C.c_int, vp]
+    lib.oracle_search_code.restype = C.c_int
+    lib.oracle_search_code.argtypes = [C.c_int, C.c_int]
+    lib.oracle_replica_time.argtypes = [C.c_double, C.c_int, C.c_int, vp]
+    lib.oracle_lo_table.argtypes = [C.c_double, C.c_double, C.c_int, vp]
+    return lib
+
+
+_L = None
+
+
+def lib() -> C.CDLL:
+    global _L
+    if _L is None:
+        _L = _lib()
+    return _L
+
+
+def cacode_chips(sv: int) -> np.ndarray:
+    out = np.zeros(1023, np.uint8)
+    lib().oracle_cacode_chips(sv, out.ctypes.data)
+    return out
+
+
+def search_code(sv: int, g1: int) -> int:
+    return lib().oracle_search_code(sv, g1)
+
+
+def replica_time(fs: float, sv: int, n: int = 40000) -> np.ndarray:
+    out = np.zeros(n, np.float32)
+    lib().oracle_replica_time(fs, sv, n, out.ctypes.data)
+    return out
+
+
+def lo_table(fc: float, fs: float, n: int = 40960) -> np.ndarray:
+    out = np.zeros(n, np.uint8)
+    lib().oracle_lo_table(fc, fs, n, out.ctypes.data)
+    return out
+
+
+class Oracle:
+    """C restatement of SearchInit()/Sample()/Correlate() (see gpsacq_oracle.c for the line map)."""
+
+    def __init__(self, fc: float, fs: float, max_fo: float = 5000.0, fft_len: int = 40000, fft_f64: bool = True):
+        self._l = lib()
+        self._h = self._l.oracle_create(fc, fs, max_fo, fft_len, 1 if fft_f64 else 0)
+        if not self._h:
+            raise MemoryError("oracle_create failed")
+        self.n = self._l.oracle_fft_len(self._h)
+        self.n_doppler = self._l.oracle_num_doppler(self._h)
+        self.dmax = (self.n_doppler - 1) // 2
+        self.window = self._l.oracle_window(self._h)
+        self.chunk_bytes = self._l.oracle_chunk_bytes(self._h)
+
+    def close(self):
+        if self._h:
+            self._l.oracle_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def code_spectrum(self, sv: int) -> np.ndarray:
+        p = self._l.oracle_code_spectrum(self._h, sv)
+        return np.ctypeslib.as_array(C.cast(p, C.POINTER(C.c_float)), shape=(2 * self.n,)).view(np.complex64).copy()
+
+    def sample(self, chunk) -> np.ndarray:
+        buf = np.ascontiguousarray(np.frombuffer(chunk, np.uint8))
+        out = np.zeros(self.n, np.complex64)
+        self._l.oracle_sample(self._h, buf.ctypes.data, out.ctypes.data)
+        return out
+
+    def cells(self, chunk, sv: int):
+        buf = np.ascontiguousarray(np.frombuffer(chunk, np.uint8))
+        mp = np.zeros(self.n_doppler, np.float32)
+        mi = np.zeros(self.n_doppler, np.int32)
+        tp = np.zeros(self.n_doppler, np.float32)
+        self._l.oracle_cells(self._h, buf.ctypes.data, sv, mp.ctypes.data, mi.ctypes.data, tp.ctypes.data)
+        return mp, mi, tp
+
+    def search_blocks(self, bits, sv_of_block=None) -> np.ndarray:
+        buf = np.ascontiguousarray(np.frombuffer(bits, np.uint8) if not isinstance(bits, np.ndarray) else bits)
+        nb = buf.size // self.chunk_bytes
+        out = np.zeros(nb, PEAK_DTYPE)
+        svp = None
+        if sv_of_block is not None:
+            sv = np.ascontiguousarray(sv_of_block, np.int32)
+            svp = sv.ctypes.data
+        rc = self._l.oracle_search_blocks(self._h, buf.ctypes.data, nb, svp, out.ctypes.data)
+        if rc:
+            raise MemoryError("oracle_search_blocks failed")
+        return out
+
+
+def mkl_env() -> dict:
+    """Environment that makes the fftw3.h stand-in use MKL (exported by torch's libtorch_cpu.so)."""
+    env = dict(os.environ)
+    try:
+        import torch  # only to locate the library
+        p = Path(torch.__file__).parent / "lib" / "libtorch_cpu.so"
+        if p.exists():
+            env.update(ORACLE_FFT="mkl", ORACLE_MKL_LIB=str(p), MKL_NUM_THREADS="1", OMP_NUM_THREADS="1")
+    except Exception:
+        pass
+    return env
+
+
+def ref_available() -> bool:
+    return (HERE / "_ref" / "libref_harness.so").exists()
+
+
+class RefHarness:
+    """The real reference (c/search_offline.cpp, unmodified) behind extern "C" probes.
+    One instance per process: the reference keeps its state in file statics."""
+
+    def __init__(self, fc: float, fs: float, max_fo: float = 5000.0):
+        p = HERE / "_ref" / "libref_harness.so"
+        if not p.exists():
+            raise FileNotFoundError(f"{p}: build with `make -C oracle` where /root/reference exists")
+        self._l = C.CDLL(str(p))
+        vp = C.c_void_p
+        self._l.ref_init.restype = C.c_int
+        self._l.ref_init.argtypes = [C.c_double, C.c_double, C.c_double]
+        self._l.ref_fft_backend.restype = C.c_char_p
+        self._l.ref_get_code.argtypes = [C.c_int, vp]
+        self._l.ref_sample.restype = C.c_int
+        self._l.ref_sample.argtypes = [vp, C.c_size_t, vp]
+        self._l.ref_search_blocks.restype = C.c_int
+        self._l.ref_search_blocks.argtypes = [vp, C.c_size_t, C.c_int, vp, vp, vp, vp]
+        self._l.ref_search_code.restype = C.c_int
+        self._l.ref_search_code.argtypes = [C.c_int, C.c_int]
+        if self._l.ref_init(fc, fs, max_fo) != 0:
+            raise RuntimeError("reference SearchInit() failed")
+        self.n = 40000
+        self.chunk_bytes = 5120
+
+    @property
+    def fft_backend(self) -> str:
+        return self._l.ref_fft_backend().decode()
+
+    def code_spectrum(self, sv: int) -> np.ndarray:
+        out = np.zeros(self.n, np.complex64)
+        self._l.ref_get_code(sv, out.ctypes.data)
+        return out
+
+    def sample(self, chunk) -> np.ndarray:
+        buf = np.ascontiguousarray(np.frombuffer(chunk, np.uint8))
+        out = np.zeros(self.n, np.complex64)
+        if self._l.ref_sample(buf.ctypes.data, buf.size, out.ctypes.data) != 0:
+            raise RuntimeError("reference Sample() ran out of data")
+        return out
+
+    def search_blocks(self, bits, sv_of_block=None) -> np.ndarray:
+        buf = np.ascontiguousarray(np.frombuffer(bits, np.uint8) if not isinstance(bits, np.ndarray) else bits)
+        nb = buf.size // self.chunk_bytes
+        snr = np.zeros(nb, np.float32)
+        lo = np.zeros(nb, np.int32)
+        ca = np.zeros(nb, np.int32)
+        svp = None
+        if sv_of_block is not None:
+            sv = np.ascontiguousarray(sv_of_block, np.int32)
+            svp = sv.ctypes.data
+        done = self._l.ref_search_blocks(buf.ctypes.data, buf.size, nb, svp, snr.ctypes.data, lo.ctypes.data, ca.ctypes.data)
+        if done != nb:
+            raise RuntimeError(f"reference stopped after {done} of {nb} chunks")
+        out = np.zeros(nb, PEAK_DTYPE)
+        out["snr"], out["lo_shift"], out["ca_shift"] = snr, lo, ca
+        out["sv"] = np.arange(nb) % 32 if sv_of_block is None else np.asarray(sv_of_block)
+        out["flags"] = (~(snr < 25)).astype(np.int32)
+        return out
+
+    def search_code(self, sv: int, g1: int) -> int:
+        return self._l.ref_search_code(sv, g1)

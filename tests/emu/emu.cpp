@@ -1,0 +1,103 @@
+// tests/emu/emu.cpp -- TEST INFRASTRUCTURE ONLY.
+//
+// CPU replay of the per-thread code of the CUDA kernels (csrc/ga_fft3.h is
+// written __host__ __device__): every "thread" of a pass is run in a loop, a
+// pass boundary is where the kernel has a __syncthreads().  This lets the index
+// algebra, twiddles and butterflies be checked against numpy in the GPU-less
+// development container.  It is never part of the product: the product path is
+// the nvcc build of the same headers and fails loudly without a GPU.
+#include <vector>
+#include <cstring>
+#include "ga_fft3.h"
+#include "ga_tables.h"
+
+using namespace ga;
+
+template <class G>
+static void emu_cell_t(const cf *xd_blk, const cf *cext_sv, int dop, int wlen, cf *y, float *best, int *besti, float *sum)
+{
+    constexpr int NW = G::RC;
+    std::vector<cf> tw = make_tw(G::N), ktab = make_ktab<G>();
+    std::vector<cf> sm((size_t)G::SMEM_ELEMS);
+    std::vector<cf> acc((size_t)G::NC * NW, mk(0, 0));
+    for (int s = 0; s < G::N1; s++) {
+        int sp, eoff;
+        cell_sub_offsets<G>(s, dop, sp, eoff);
+        const cf *xs = xd_blk + (size_t)s * G::N2;
+        const cf *cs = cext_sv + (size_t)sp * 2 * G::N2 + eoff;
+        for (int j = 0; j < G::NA; j++) cell_passA<G>(j, s, xs, cs, tw.data(), sm.data());
+        for (int j = 0; j < G::NB; j++) passB<G, +1>(j, s, tw.data(), sm.data());
+        for (int j = 0; j < G::NC; j++) {
+            cf a[NW];
+            memcpy(a, &acc[(size_t)j * NW], sizeof a);
+            cell_passC_acc<G, NW>(j, sm.data(), ktab.data() + (size_t)s * G::RC, a);
+            memcpy(&acc[(size_t)j * NW], a, sizeof a);
+        }
+    }
+    float b = 0, sm_ = 0; int bi = 0;
+    for (int j = 0; j < G::NC; j++) {
+        cf a[NW];
+        memcpy(a, &acc[(size_t)j * NW], sizeof a);
+        const int u = j / G::RB, v = j - u * G::RB, tau0 = u + G::RA * v;
+        for (int w = 0; w < NW; w++) y[tau0 + G::OUT_STRIDE * w] = a[w];
+        cell_peak_thread<G, NW>(a, tau0, wlen, b, bi, sm_);
+    }
+    *best = b; *besti = bi; *sum = sm_;
+}
+
+struct TimeSrc { const cf *x; cf operator()(int n) const { return x[n]; } };
+
+template <class G>
+static void emu_fwd_t(const cf *x, int s, cf *out)
+{
+    std::vector<cf> tw = make_tw(G::N), k1 = make_k1tab<G>();
+    std::vector<cf> sm((size_t)G::SMEM_ELEMS);
+    TimeSrc src{x};
+    for (int j = 0; j < G::NA; j++) fwd_passA<G>(j, s, src, k1.data() + (size_t)s * G::N1, tw.data(), sm.data());
+    for (int j = 0; j < G::NB; j++) passB<G, -1>(j, 0, tw.data(), sm.data());
+    for (int j = 0; j < G::NC; j++) {
+        cf p[G::RC];
+        const int tau0 = passC<G, -1>(j, sm.data(), p);
+        for (int w = 0; w < G::RC; w++) out[tau0 + G::OUT_STRIDE * w] = p[w];
+    }
+}
+
+typedef Geom<5, 20, 20, 20> G8000;
+typedef Geom<4, 25, 20, 20> G10000;
+typedef Geom<10, 20, 20, 10> G4000;
+
+extern "C" {
+
+int emu_geom(int id, int *n1, int *n2)
+{
+    switch (id) {
+    case 0: *n1 = G8000::N1; *n2 = G8000::N2; return 0;
+    case 1: *n1 = G10000::N1; *n2 = G10000::N2; return 0;
+    case 2: *n1 = G4000::N1; *n2 = G4000::N2; return 0;
+    }
+    return -1;
+}
+
+// xd_blk: conj(X) decimated [N1][N2]; cext_sv: [N1][2*N2]; y: N2 complex outputs
+int emu_cell(int id, const float *xd_blk, const float *cext_sv, int dop, int wlen, float *y, float *best, int *besti, float *sum)
+{
+    switch (id) {
+    case 0: emu_cell_t<G8000>((const cf *)xd_blk, (const cf *)cext_sv, dop, wlen, (cf *)y, best, besti, sum); return 0;
+    case 1: emu_cell_t<G10000>((const cf *)xd_blk, (const cf *)cext_sv, dop, wlen, (cf *)y, best, besti, sum); return 0;
+    case 2: emu_cell_t<G4000>((const cf *)xd_blk, (const cf *)cext_sv, dop, wlen, (cf *)y, best, besti, sum); return 0;
+    }
+    return -1;
+}
+
+// x: N complex time samples; out: N2 values X[N1*q+s]
+int emu_fwd(int id, const float *x, int s, float *out)
+{
+    switch (id) {
+    case 0: emu_fwd_t<G8000>((const cf *)x, s, (cf *)out); return 0;
+    case 1: emu_fwd_t<G10000>((const cf *)x, s, (cf *)out); return 0;
+    case 2: emu_fwd_t<G4000>((const cf *)x, s, (cf *)out); return 0;
+    }
+    return -1;
+}
+
+}
