@@ -1,0 +1,248 @@
+"""GPU parity tests (run with `-m gpu` on a B200): the CUDA engine, called through the C ABI,
+against (a) golden vectors produced by the unmodified reference and (b) the CPU oracle."""
+import importlib
+import subprocess
+
+import numpy as np
+import pytest
+
+from conftest import CAPTURES, ROOT, SNR_RTOL, compare_peaks, compare_runs, parse_stdout, strip_banner
+
+pytestmark = pytest.mark.gpu
+PKG = ROOT / "gnss-gps-sdr_b200"
+
+
+@pytest.fixture(scope="module")
+def engines(ga):
+    made = {}
+
+    def get(fc, fs, max_fo=5000.0, **kw):
+        key = (fc, fs, max_fo, tuple(sorted(kw.items())))
+        if key not in made:
+            made[key] = ga.Acquisition(fc, fs, max_fo, **kw)
+        return made[key]
+
+    yield get
+    for a in made.values():
+        a.close()
+
+
+@pytest.fixture(scope="module")
+def siggen(ga):
+    return importlib.import_module("gnss_gps_sdr_b200.siggen")
+
+
+# ---- SearchInit(): replicas -------------------------------------------------------------------
+@pytest.mark.parametrize("fs", [5.456e6, 8.184e6, 2.8e6, 10e6])
+def test_replica_time_bit_exact(engines, oracle_mod, fs):
+    """Code NCO + chip-edge blend (c/search_offline.cpp:84-103) is float-for-float identical."""
+    acq = engines(fs / 4, fs)
+    for sv in range(32):
+        a, b = acq.replica_time(sv), oracle_mod.replica_time(fs, sv)
+        assert np.array_equal(a.view(np.uint32), b.view(np.uint32)), f"PRN {sv + 1}"
+
+
+@pytest.mark.parametrize("name", list(CAPTURES))
+def test_replica_spectra_vs_reference(engines, oracle_mod, name):
+    c = CAPTURES[name]
+    acq = engines(c["fc"], c["fs"])
+    p = np.load(c["probe"])
+    o = oracle_mod.Oracle(c["fc"], c["fs"])
+    for sv in range(32):
+        s = acq.replica_spectrum(sv)
+        scale = np.abs(s).max()
+        assert np.abs(s[p["idx"]] - p["code"][sv]).max() <= 3e-6 * scale          # reference code[sv]
+        assert abs(np.abs(s).astype(np.float64).sum() / p["code_abs_sum"][sv] - 1) < 1e-6
+        if sv % 8 == 0:
+            assert np.abs(s - o.code_spectrum(sv)).max() <= 3e-6 * scale           # full spectrum vs oracle
+
+
+# ---- Sample(): unpack + mix + forward FFT ----------------------------------------------------------
+@pytest.mark.parametrize("name", list(CAPTURES))
+def test_block_spectrum_vs_reference(engines, oracle_mod, name):
+    c = CAPTURES[name]
+    acq = engines(c["fc"], c["fs"])
+    data = c["bin"].read_bytes()
+    acq.search_blocks(data[: 40 * 5120])
+    p = np.load(c["probe"])
+    o = oracle_mod.Oracle(c["fc"], c["fs"])
+    x0 = acq.block_spectrum(0)
+    assert np.abs(x0[p["idx"]] - p["block0"]).max() <= 3e-6 * np.abs(x0).max()    # reference fwd_buf
+    for b in (0, 17, 39):
+        xo = o.sample(data[b * 5120:(b + 1) * 5120])
+        assert np.abs(acq.block_spectrum(b) - xo).max() <= 3e-6 * np.abs(xo).max()
+
+
+# ---- Correlate(): per-cell statistics ------------------------------------------------------------
+@pytest.mark.parametrize("name", list(CAPTURES))
+def test_cell_stats_vs_oracle(engines, oracle_mod, name):
+    c = CAPTURES[name]
+    acq = engines(c["fc"], c["fs"])
+    data = c["bin"].read_bytes()[: 32 * 5120]
+    acq.search_blocks(data)
+    o = oracle_mod.Oracle(c["fc"], c["fs"])
+    for b in (0, 7, 20, 31):
+        cs = acq.cell_stats(b)
+        mp, mi, tp = o.cells(data[b * 5120:(b + 1) * 5120], b)
+        assert np.abs(cs["max_pwr"] / mp - 1).max() <= 2e-5
+        assert np.abs(cs["tot_pwr"] / tp - 1).max() <= 2e-5
+        # argmax exact; a differing index is tolerated only for a genuine float tie
+        diff = cs["max_idx"] != mi
+        assert diff.sum() <= 1 and np.all(np.abs(cs["max_pwr"][diff] / mp[diff] - 1) < 1e-6)
+
+
+# ---- whole path vs the reference's own outputs -----------------------------------------------------
+@pytest.mark.parametrize("name", list(CAPTURES))
+def test_peaks_vs_reference_golden(engines, name):
+    """(snr, lo_shift, ca_shift) of every chunk of the fixture vs what the unmodified reference's
+    Sample()+Correlate() returned (tests/golden/ref_peaks_*.npy)."""
+    c = CAPTURES[name]
+    acq = engines(c["fc"], c["fs"])
+    got = acq.search_blocks(c["bin"].read_bytes())
+    ref = np.load(c["peaks"])
+    assert len(got) == len(ref) == c["runs"] * 32
+    worst = compare_peaks(got, ref)
+    assert worst < 1e-3
+    assert np.array_equal(got["sv"], np.arange(len(got)) % 32)
+
+
+@pytest.mark.parametrize("name", list(CAPTURES))
+def test_search_task_text_vs_golden_stdout(ga, engines, name):
+    c = CAPTURES[name]
+    acq = engines(c["fc"], c["fs"])
+    text = ga.search_task_text(acq, str(c["bin"]), runs_per_batch=3)
+    got_runs, tail = parse_stdout(text)
+    ref_runs, _ = parse_stdout(strip_banner(c["stdout"].read_text()))
+    assert tail == ["run out of file!"] and len(got_runs) == c["runs"]
+    compare_runs(got_runs, ref_runs[: c["runs"]])
+
+
+@pytest.mark.parametrize("name", list(CAPTURES))
+def test_gps_test_binary_vs_golden_stdout(name):
+    """The C++ drop-in `gps_test` (reference CLI) end to end."""
+    c = CAPTURES[name]
+    subprocess.run(["make", "-s", "gps_test"], cwd=ROOT, check=True)
+    r = subprocess.run([str(PKG / "c" / "gps_test"), str(c["bin"]), repr(c["fc"]), repr(c["fs"]), "5000"],
+                       capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr
+    golden = c["stdout"].read_text()
+    assert r.stdout.split("\n")[:6] == golden.split("\n")[:6]                       # banner byte-identical
+    got_runs, tail = parse_stdout(strip_banner(r.stdout))
+    ref_runs, _ = parse_stdout(strip_banner(golden))
+    assert tail == ["run out of file!"]
+    compare_runs(got_runs, ref_runs[: c["runs"]])
+
+
+def test_full_capture_if_present(ga, engines):
+    """All 340 runs of the Nottingham capture when the 55 MB file travelled with the repo
+    (oracle/_ref/data/, git-ignored)."""
+    f = ROOT / "oracle" / "_ref" / "data" / "gps.samples.1bit.I.fs5456.if4092.bin"
+    if not f.exists():
+        pytest.skip("full capture not staged")
+    c = CAPTURES["nottingham"]
+    text = ga.search_task_text(engines(c["fc"], c["fs"]), str(f))
+    got_runs, tail = parse_stdout(text)
+    ref_runs, _ = parse_stdout(strip_banner(c["stdout"].read_text()))
+    assert len(got_runs) == 340 and tail == ["run out of file!"]
+    compare_runs(got_runs, ref_runs)
+
+
+# ---- batching, ragged sizes, explicit PRN maps --------------------------------------------------------
+def test_batching_and_ragged_sizes(ga, engines):
+    c = CAPTURES["nottingham"]
+    data = c["bin"].read_bytes()
+    base = engines(c["fc"], c["fs"]).search_blocks(data)                # 128 chunks, one batch
+    small = ga.Acquisition(c["fc"], c["fs"], max_blocks=48)             # forces 48+48+32
+    try:
+        again = small.search_blocks(data)
+        assert again.tobytes() == base.tobytes()                        # bit-identical regardless of batching
+        assert len(small.search_blocks(b"")) == 0                       # empty input
+        one = small.search_blocks(data[:5120 + 100])                    # ragged tail ignored
+        assert len(one) == 1 and one.tobytes() == base[:1].tobytes()
+        # explicit PRN map: search chunk 0 for every PRN; entry 0 equals the REF result
+        sv = np.arange(32, dtype=np.int32)
+        allsv = small.search_blocks(data[:5120] * 32, sv)
+        assert allsv[0].tobytes() == base[0].tobytes() and np.array_equal(allsv["sv"], sv)
+        with pytest.raises(ga.GpsAcqError):
+            small.search_blocks(data[:5120], np.array([32], np.int32))
+    finally:
+        small.close()
+
+
+def test_rejects_unsupported_configs(ga):
+    with pytest.raises(ga.GpsAcqError, match="not supported"):
+        ga.Acquisition(4e6, 16.368e6)
+    with pytest.raises(ga.GpsAcqError):
+        ga.Acquisition(4e6, -1.0)
+
+
+# ---- other sampling rates, synthetic captures (no reference fixture exists) --------------------------------
+@pytest.mark.parametrize("fs,fc,seed", [(2.8e6, 0.62e6, 1575420001), (10e6, 2.6e6, 3), (5.456e6, 4.092e6, 1575420000)])
+def test_synthetic_vs_oracle(engines, oracle_mod, siggen, fs, fc, seed):
+    sats = siggen.default_constellation(fs, seed=seed)
+    bits = siggen.synth_capture(40960 * 32, fs, fc, sats, seed=seed)
+    acq = engines(fc, fs)
+    got = acq.search_blocks(bits)
+    ref = oracle_mod.Oracle(fc, fs).search_blocks(bits)
+    compare_peaks(got, ref)
+    for s in sats:                      # every generated satellite is found at its Doppler bin
+        p = got[s["prn"] - 1]
+        assert p["snr"] >= 25 and abs(p["lo_shift"] - s["doppler_hz"] * 40000 / fs) <= 1.0
+
+
+def test_max_fo_changes_the_doppler_grid(engines, oracle_mod, siggen):
+    fs, fc = 5.456e6, 4.092e6
+    sats = [dict(prn=9, doppler_hz=7300.0, code_phase_chips=100.25, amp=0.3)]
+    bits = siggen.synth_capture(40960 * 9, fs, fc, sats, noise_sigma=1.0, seed=5)
+    acq = engines(fc, fs, 10000.0)
+    assert acq.n_doppler == 2 * int(10000.0 * 40000 / fs) + 1
+    got = acq.search_blocks(bits)
+    ref = oracle_mod.Oracle(fc, fs, 10000.0).search_blocks(bits)
+    compare_peaks(got, ref)
+    assert got[8]["lo_shift"] == round(7300.0 * 40000 / fs)
+
+
+# ---- size-independent properties at full batch size ------------------------------------------------------
+def test_full_batch_properties(engines, siggen):
+    """512 chunks x 73 bins: identical (chunk, PRN) pairs give bit-identical records wherever they
+    sit in the batch; the complement of a capture (all bits flipped = signal negated) gives the
+    same powers; and records do not depend on neighbours."""
+    c = CAPTURES["nottingham"]
+    data = np.frombuffer(c["bin"].read_bytes(), np.uint8).reshape(128, 5120)
+    rng = np.random.default_rng(11)
+    pick = rng.integers(0, 128, 512)
+    sv = rng.integers(0, 32, 512).astype(np.int32)
+    acq = engines(c["fc"], c["fs"])
+    got = acq.search_blocks(np.ascontiguousarray(data[pick]).reshape(-1), sv)
+    key = {}
+    for i in range(512):
+        k = (int(pick[i]), int(sv[i]))
+        if k in key:
+            j = key[k]
+            assert got[i].tobytes() == got[j].tobytes()
+        key[k] = i
+    neg = acq.search_blocks(np.ascontiguousarray(~data[pick[:64]]).reshape(-1), sv[:64])
+    assert np.array_equal(neg["lo_shift"], got["lo_shift"][:64]) and np.array_equal(neg["ca_shift"], got["ca_shift"][:64])
+    assert np.allclose(neg["snr"], got["snr"][:64], rtol=1e-5)
+
+
+# ---- device-pointer API on torch's stream ---------------------------------------------------------------
+def test_device_api_on_torch_stream(ga, engines):
+    import torch
+    c = CAPTURES["nottingham"]
+    acq = engines(c["fc"], c["fs"])
+    data = c["bin"].read_bytes()[: 64 * 5120]
+    host = acq.search_blocks(data)
+    dev = torch.device("cuda", acq.info["device"])
+    bits = torch.frombuffer(bytearray(data), dtype=torch.uint8).to(dev)
+    out = torch.zeros(64 * 32, dtype=torch.uint8, device=dev)
+    stream = torch.cuda.Stream(device=dev)
+    with torch.cuda.stream(stream):
+        acq.set_stream(stream.cuda_stream)
+        acq.search_blocks_device(bits.data_ptr(), 64, None, out.data_ptr())
+    stream.synchronize()
+    acq.set_stream(None)
+    got = np.frombuffer(out.cpu().numpy().tobytes(), ga.PEAK_DTYPE)
+    assert got.tobytes() == host.tobytes()
+    t = acq.stage_times()
+    assert t["cells_ms"] > 0 and t["total_ms"] >= t["cells_ms"]

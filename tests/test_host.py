@@ -1,0 +1,167 @@
+"""CPU-only: host logic, the C ABI's exported symbols, the C++ host tree, and the CPU replay of
+the kernel arithmetic (tests/emu) against numpy."""
+import ctypes
+import re
+import subprocess
+
+import numpy as np
+import pytest
+
+from conftest import CAPTURES, ROOT, parse_stdout, strip_banner
+
+PKG = ROOT / "gnss-gps-sdr_b200"
+
+
+@pytest.fixture(scope="module", autouse=True)
+def built():
+    subprocess.run(["make", "-s", "lib", "gps_test", "emu"], cwd=ROOT, check=True)
+
+
+def test_c_abi_exports_every_declared_symbol(ga):
+    header = (ROOT / "include" / "gpsacq.h").read_text()
+    declared = set(re.findall(r"\b(gpsacq_[a-z_]+)\s*\(", header))
+    declared -= {"gpsacq_cfg", "gpsacq_peak", "gpsacq_cell", "gpsacq_info"}
+    lib = ctypes.CDLL(str(ga.lib_path()))
+    for name in sorted(declared):
+        assert hasattr(lib, name), f"{name} declared in include/gpsacq.h but not exported"
+    from gnss_gps_sdr_b200 import acq
+    assert set(acq.ABI_SYMBOLS) == declared
+    ga.load_library()
+
+
+def test_struct_layouts_match_header(ga):
+    assert ga.PEAK_DTYPE.itemsize == 32 and ga.CELL_DTYPE.itemsize == 16
+    assert ga.PEAK_DTYPE.fields["ca_shift"][1] == 16 and ga.PEAK_DTYPE.fields["flags"][1] == 24
+
+
+def test_no_cpu_fallback(ga, gpu_available):
+    if gpu_available:
+        pytest.skip("a GPU is present")
+    with pytest.raises(ga.GpsAcqError, match="no CUDA device|CUDA"):
+        ga.Acquisition(4.092e6, 5.456e6)
+
+
+def test_product_never_imports_oracle():
+    """The oracle is the checker; nothing under the package or include/ may import, link or dlopen it."""
+    banned = re.compile(r"import\s+oracle|from\s+oracle|liboracle|libref_harness|gps_test_ref|fft_mixed|libemu")
+    files = [p for ext in ("*.py", "*.cu", "*.cuh", "*.h", "*.cpp", "akefile") for p in PKG.rglob(ext)]
+    files += [ROOT / "include" / "gpsacq.h", ROOT / "gpsacq_loader.py"]
+    assert len(files) > 10
+    for p in files:
+        assert not banned.search(p.read_text()), p
+
+
+def test_format_run_reproduces_reference_stdout(ga):
+    """SearchTask()'s report (c/search_offline.cpp:264-287) from the reference's own peak records."""
+    for name, c in CAPTURES.items():
+        ref = np.load(c["peaks"])
+        pk = np.zeros(len(ref), ga.PEAK_DTYPE)
+        for f in ("snr", "lo_shift", "ca_shift", "sv"):
+            pk[f] = ref[f]
+        text = "".join(ga.format_run(r, pk[32 * r:32 * r + 32]) for r in range(c["runs"]))
+        golden = strip_banner(c["stdout"].read_text())
+        assert golden.startswith(text), name          # byte-identical for the runs covered by the fixture
+
+
+class _FakeAcq:
+    """Stands in for the engine to test SearchTask()'s file traversal without a GPU."""
+    chunk_bytes = 5120
+
+    def __init__(self, ga, peaks):
+        self.ga, self.peaks, self.calls = ga, peaks, []
+
+    def search_blocks(self, bits, sv_of_block=None):
+        n = len(bits) // 5120
+        start = sum(self.calls)
+        self.calls.append(n)
+        out = np.zeros(n, self.ga.PEAK_DTYPE)
+        for f in ("snr", "lo_shift", "ca_shift", "sv"):
+            out[f] = self.peaks[f][start:start + n]
+        return out
+
+
+def test_search_task_traversal(ga, tmp_path):
+    c = CAPTURES["nottingham"]
+    ref = np.load(c["peaks"])
+    data = c["bin"].read_bytes()
+    # 3 full runs + a ragged tail: the partial run is discarded with "run out of file!"
+    f = tmp_path / "ragged.bin"
+    f.write_bytes(data[: 3 * 163840 + 7777])
+    fake = _FakeAcq(ga, ref)
+    text = ga.search_task_text(fake, str(f), runs_per_batch=2)
+    runs, tail = parse_stdout(text)
+    assert [r["run"] for r in runs] == [0, 1, 2] and tail == ["run out of file!"]
+    assert fake.calls == [64, 32]
+    assert strip_banner(c["stdout"].read_text()).startswith(text[: text.index("run out")])
+    # exact multiple of a run: still ends with the message (fread returns 0 on the next Sample())
+    f.write_bytes(data[: 2 * 163840])
+    text = ga.search_task_text(_FakeAcq(ga, ref), str(f), runs_per_batch=2)
+    assert text.endswith("run out of file!\n") and len(parse_stdout(text)[0]) == 2
+    # empty file and missing file
+    f.write_bytes(b"")
+    assert ga.search_task_text(_FakeAcq(ga, ref), str(f)) == "run out of file!\n"
+    assert ga.search_task_text(_FakeAcq(ga, ref), str(tmp_path / "nope.bin")) == "can not open file!\n"
+
+
+def test_cxx_host_tree(tmp_path):
+    exe = tmp_path / "host_check"
+    subprocess.run(["g++", "-O1", "-std=c++17", f"-I{PKG / 'c'}", str(ROOT / "tests/host/host_check.cpp"),
+                    str(PKG / "c/search_offline.cpp"), "-o", str(exe), f"-L{PKG / 'csrc'}", "-lgpsacq",
+                    f"-Wl,-rpath,{PKG / 'csrc'}", "-lpthread"], check=True)
+    out = subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.split("\n")
+    assert out[0] == "first10 1440 ones 512 g1_after_period 1023 g1_seed 1023"     # IS-GPS-200 PRN 1
+    assert out[1] == "first10 1712 ones 512 g1_after_period 1023 g1_seed 1023"     # PRN 32
+    sc = [int(v) for v in out[2].split()[1:]]
+    assert sc[0] == 0 and 0 < sc[1] < 1023 and sc[2] == -1 and sc[3] == -1
+
+
+def test_gps_test_cli_contract(gpu_available):
+    """Banner, argument rules and exit codes of gps_test (c/test_search_offline.cpp:24-44)."""
+    exe = PKG / "c" / "gps_test"
+    golden_banner = "\n".join(CAPTURES["nottingham"]["stdout"].read_text().split("\n")[:6]) + "\n"
+    r = subprocess.run([str(exe), "a", "b"], capture_output=True, text=True)
+    assert r.returncode == 0 and r.stdout == golden_banner + "Please run with 3 arguments or without argument!\n"
+    if not gpu_available:
+        r = subprocess.run([str(exe), "x.bin", "4.092e6", "5.456e6", "5000"], capture_output=True, text=True)
+        assert r.returncode != 0 and r.stdout.startswith(golden_banner) and "SearchInit() returned" in r.stdout
+
+
+# ---- CPU replay of the kernel arithmetic ---------------------------------------------------------
+def _emu():
+    L = ctypes.CDLL(str(ROOT / "tests/emu/libemu.so"))
+    return L
+
+
+@pytest.mark.parametrize("gid,W", [(0, 5456), (1, 8184), (2, 2800)])
+def test_kernel_math_replay_matches_numpy(gid, W):
+    L = _emu()
+    fp = ctypes.POINTER(ctypes.c_float)
+    P = lambda a: a.ctypes.data_as(fp)
+    n1, n2 = ctypes.c_int(), ctypes.c_int()
+    assert L.emu_geom(gid, ctypes.byref(n1), ctypes.byref(n2)) == 0
+    N1, N2 = n1.value, n2.value
+    N = N1 * N2
+    assert N == 40000 and W <= N2
+    rng = np.random.default_rng(gid)
+    x = (rng.standard_normal(N) + 1j * rng.standard_normal(N)).astype(np.complex64)
+    X = np.fft.fft(x.astype(np.complex128))
+    for s in (0, N1 - 1):
+        out = np.zeros(N2, np.complex64)
+        L.emu_fwd(gid, P(x.view(np.float32)), s, P(out.view(np.float32)))
+        assert np.abs(out - X[s::N1]).max() <= 2e-6 * np.abs(X).max()
+    Xs = (rng.standard_normal(N) + 1j * rng.standard_normal(N)).astype(np.complex64)
+    Cc = (rng.standard_normal(N) + 1j * rng.standard_normal(N)).astype(np.complex64)
+    xd = np.conj(Xs).reshape(N2, N1).T.copy()
+    cd = Cc.reshape(N2, N1).T
+    cext = np.concatenate([cd, cd], axis=1).copy()
+    for dop in (-36, -1, 0, 5, 36):
+        # prod[k] = conj(X[k]) * C[(k - dop) mod N]  (c/search_offline.cpp:181-185), backward FFT (:187)
+        y = np.fft.ifft(np.conj(Xs.astype(np.complex128)) * np.roll(Cc.astype(np.complex128), dop)) * N
+        yy = np.zeros(N2, np.complex64)
+        best, bi, sm = ctypes.c_float(), ctypes.c_int(), ctypes.c_float()
+        L.emu_cell(gid, P(xd.view(np.float32)), P(cext.view(np.float32)), dop, W, P(yy.view(np.float32)),
+                   ctypes.byref(best), ctypes.byref(bi), ctypes.byref(sm))
+        assert np.abs(yy - y[:N2]).max() <= 2e-6 * np.abs(y).max()
+        pw = np.abs(y[:W]) ** 2
+        assert bi.value == int(pw.argmax())
+        assert abs(best.value / pw.max() - 1) < 1e-5 and abs(sm.value / pw.sum() - 1) < 1e-5

@@ -1,0 +1,106 @@
+"""CPU-only: pins the oracle (C restatement) to the reference's golden vectors."""
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+from conftest import CAPTURES, ROOT, compare_peaks, parse_stdout, strip_banner, compare_runs
+
+# IS-GPS-200 Table 3-Ia, "First 10 chips octal C/A", PRN 1..32
+IS_GPS_200_FIRST10 = [0o1440, 0o1620, 0o1710, 0o1744, 0o1133, 0o1455, 0o1131, 0o1454, 0o1626, 0o1504, 0o1642,
+                      0o1750, 0o1764, 0o1772, 0o1775, 0o1776, 0o1156, 0o1467, 0o1633, 0o1715, 0o1746, 0o1763,
+                      0o1063, 0o1706, 0o1743, 0o1761, 0o1770, 0o1774, 0o1127, 0o1453, 0o1625, 0o1712]
+
+
+def test_cacode_known_answers(oracle_mod):
+    for sv in range(32):
+        chips = oracle_mod.cacode_chips(sv)
+        first10 = int("".join(str(int(b)) for b in chips[:10]), 2)
+        assert first10 == IS_GPS_200_FIRST10[sv], f"PRN {sv + 1}"
+        assert int(chips.sum()) == 512          # balanced Gold code: 512 ones, 511 zeros
+    # distinct codes, period exactly 1023 (autocorrelation of a Gold code is {-1, 63, -65, 1023})
+    c = 1 - 2 * oracle_mod.cacode_chips(0).astype(int)
+    ac = np.array([np.dot(c, np.roll(c, k)) for k in range(1023)])
+    assert ac[0] == 1023 and set(ac[1:]) <= {-1, 63, -65}
+
+
+def test_search_code_roundtrip(oracle_mod):
+    # SearchCode(sv, g1): chips until the G1 register equals g1 (c/search_offline.cpp:205-209).
+    assert oracle_mod.search_code(0, 0x3FF) == 0            # all-ones seed
+    seen = {oracle_mod.search_code(5, g1) for g1 in range(1, 1024)}
+    assert seen == set(range(1023))                           # G1 is maximal length: every state once
+    assert oracle_mod.search_code(5, 0) == -1                 # unreachable state (reference would spin)
+
+
+def test_replica_nco_facts(oracle_mod):
+    # at 8.184 MHz chip edges land on ca_phase = 0 -> replica is exactly +-1
+    r = oracle_mod.replica_time(8.184e6, 7)
+    assert set(np.unique(r)) == {-1.0, 1.0}
+    # at 5.456 MHz ca_rate = 3/16 exactly: 40000 samples advance exactly 7500 chips
+    r = oracle_mod.replica_time(5.456e6, 0)
+    assert np.abs(r).max() <= 1.0 and (np.abs(r) < 1.0).any()
+    lo = oracle_mod.lo_table(4.092e6, 5.456e6)
+    assert np.array_equal(lo, (3 * np.arange(40960)) % 4)     # lo_rate = 3.0 exactly
+
+
+@pytest.mark.parametrize("name", list(CAPTURES))
+@pytest.mark.parametrize("fft_f64", [True, False])
+def test_oracle_matches_reference_peaks(oracle_mod, name, fft_f64):
+    c = CAPTURES[name]
+    ref = np.load(c["peaks"])
+    o = oracle_mod.Oracle(c["fc"], c["fs"], fft_f64=fft_f64)
+    nb = 64 if fft_f64 else 32                               # keep the CPU suite short
+    got = o.search_blocks(c["bin"].read_bytes()[: nb * 5120])
+    compare_peaks(got, ref[:nb], snr_rtol=2e-5)
+
+
+@pytest.mark.parametrize("name", list(CAPTURES))
+def test_oracle_matches_reference_spectra(oracle_mod, name):
+    c = CAPTURES[name]
+    p = np.load(c["probe"])
+    o = oracle_mod.Oracle(c["fc"], c["fs"])
+    for sv in range(32):
+        s = o.code_spectrum(sv)
+        assert np.abs(s[p["idx"]] - p["code"][sv]).max() <= 2e-6 * np.abs(s).max()
+        assert abs(np.abs(s).astype(np.float64).sum() / p["code_abs_sum"][sv] - 1) < 1e-6
+    x = o.sample(c["bin"].read_bytes()[:5120])
+    assert np.abs(x[p["idx"]] - p["block0"]).max() <= 2e-6 * np.abs(x).max()
+
+
+@pytest.mark.parametrize("name", list(CAPTURES))
+def test_oracle_reproduces_golden_stdout(oracle_mod, ga, name):
+    """Oracle -> SearchTask() report formatter (host logic) -> compare with gps_test's own stdout."""
+    c = CAPTURES[name]
+    ref_runs, tail = parse_stdout(strip_banner(c["stdout"].read_text()))
+    assert tail == ["run out of file!"]
+    o = oracle_mod.Oracle(c["fc"], c["fs"])
+    pk = o.search_blocks(c["bin"].read_bytes()[: 2 * 32 * 5120])
+    text = "".join(ga.format_run(r, pk[32 * r: 32 * r + 32]) for r in range(2))
+    got_runs, _ = parse_stdout(text)
+    compare_runs(got_runs, ref_runs[:2])
+
+
+def test_golden_stdout_is_complete():
+    runs, _ = parse_stdout(strip_banner(CAPTURES["nottingham"]["stdout"].read_text()))
+    assert len(runs) == 340 and runs[-1]["run"] == 339      # 55,791,616 B / 163,840 B
+    assert runs[0]["ca"] == [1057, 4848, 4963, 5029, 478, 1148, 3283, 1331, 3005, 4049]
+    runs, _ = parse_stdout(strip_banner(CAPTURES["gps_sig"]["stdout"].read_text()))
+    assert len(runs) == 12 and 7 in runs[0]["sv"]
+
+
+def test_live_reference_agrees_with_oracle(oracle_mod):
+    """When oracle/_ref was built here (or travelled prebuilt), drive the real reference TU."""
+    if not oracle_mod.ref_available():
+        pytest.skip("oracle/_ref/libref_harness.so not built (needs /root/reference)")
+    code = (
+        "import sys; sys.path.insert(0, %r); import numpy as np, oracle\n"
+        "d = open(%r,'rb').read()[:8*5120]\n"
+        "r = oracle.RefHarness(4.092e6, 5.456e6); o = oracle.Oracle(4.092e6, 5.456e6)\n"
+        "sv = np.array([0, 4, 12, 15, 20, 22, 24, 28], np.int32)\n"
+        "a = r.search_blocks(d, sv); b = o.search_blocks(d, sv)\n"
+        "assert np.array_equal(a['lo_shift'], b['lo_shift']) and np.array_equal(a['ca_shift'], b['ca_shift'])\n"
+        "assert np.abs(a['snr']/b['snr']-1).max() < 1e-5\n"
+        "assert r.search_code(3, 0x2AA) == oracle.search_code(3, 0x2AA)\n"
+    ) % (str(ROOT / "oracle"), str(CAPTURES["nottingham"]["bin"]))
+    subprocess.run([sys.executable, "-c", code], check=True)
