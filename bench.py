@@ -1,0 +1,341 @@
+#!/usr/bin/env python
+"""bench.py -- PRN x Doppler correlations/sec of the B200 GPS L1 C/A acquisition engine.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W]            # this repo's engine
+    python bench.py --impl reference [--gpus N] [--steps K] ...    # the reference's own CPU path
+
+Workload (config.workload): BASELINE.json configs[1] input parameters -- 32 PRN, +-5 kHz,
+fs = 5.456 MHz, IF = 4.092 MHz, synthetic 1-bit IQ -- searched with the REFERENCE's grid
+semantics (N = 40000-point coherent window, 73 Doppler bins of fs/N = 136.4 Hz, one 5120-byte
+chunk per PRN; c/search_offline.cpp:176,239-246), because that is the only grid on which parity
+with gps_test is defined and the only one the reference arm can run.
+
+A "step" is one batch of 16 runs = 512 chunks x 73 bins = 37,376 correlations per GPU: forward
+FFT kernel, cell kernel (shifted conj-multiply + pruned backward FFT + |.|^2 + peak), best-over-
+Doppler kernel, and for N > 1 one NCCL all-gather of the 512 32-byte peak records per rank.
+Ranks work on different runs of the stream (weak scaling, no data-path collective).
+
+value   : device-resident inputs (packed bits already in HBM), CUDA events on the launching stream.
+e2e     : same step through the host-buffer C-ABI call gpsacq_search_blocks(): pinned host bits ->
+          H2D -> kernels -> D2H peak records, host synchronised, every step.
+roofline: the cell kernel alone.  achieved = 640,016 algorithmic bytes per correlation (one read
+          of the 40000-point complex64 block spectrum + one of the replica spectrum + a 16-byte
+          record) x correlations per launch / average launch time from CUDA
+          events recorded around the launch inside libgpsacq (gpsacq_stage_times()).
+          peak = MEASURED_PEAKS.json hbm_gbs.  The operands are L2-resident after first touch, so
+          the real DRAM traffic is far below the algorithmic bytes (roofline.traffic, from ncu).
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+FC, FS, MAX_FO = 4.092e6, 5.456e6, 5000.0
+RUNS_PER_STEP = 16
+CHUNK = 5120
+N_BATCHES = 4                       # distinct input batches cycled through the steps
+METRIC = "PRN×Doppler correlations/sec"
+UNIT = "correlations/s"
+
+
+def make_batches(n_batches: int, seed: int):
+    import gpsacq_loader
+    import importlib
+    gpsacq_loader.load()
+    sg = importlib.import_module("gnss_gps_sdr_b200.siggen")
+    sats = sg.default_constellation(FS, seed=1575420000)
+    n_samples = RUNS_PER_STEP * 32 * CHUNK * 8
+    return [sg.synth_capture(n_samples, FS, FC, sats, seed=seed * 1000 + b) for b in range(n_batches)]
+
+
+def workload_config(n_gpus: int):
+    return {"workload": "C1-REF: synthetic 1-bit IF fs=5.456MHz if=4.092MHz, 32 PRN x 73 Doppler bins "
+                        "(+-5 kHz @ 136.4 Hz), N=40000 coherent (7.33 ms), 16 runs (512 chunks) per GPU per step",
+            "correlations_per_step_per_gpu": RUNS_PER_STEP * 32 * 73,
+            "sharding": f"runs of the stream split over {n_gpus} GPU(s); NCCL all-gather of peak records"
+                        if n_gpus > 1 else "single GPU",
+            "l2_policy": "inputs larger than L2: each step's cell-kernel operands are 164 MB of block spectra "
+                         "+ 20 MB of replica spectra (> 126 MB L2); 4 distinct input batches are cycled"}
+
+
+# -------------------------------------------------------------------------------------------------
+class ClockSampler(threading.Thread):
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        super().__init__(daemon=True)
+        self.index, self.rows, self._halt = index, [], threading.Event()
+
+    def run(self):
+        while not self._halt.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                      "-i", str(self.index)], capture_output=True, text=True, timeout=5).stdout
+                self.rows.append([c.strip() for c in out.strip().split(",")])
+            except Exception:
+                pass
+            self._halt.wait(0.1)
+
+    def finish(self):
+        self._halt.set()
+        self.join(timeout=6)
+        rows = [r for r in self.rows if len(r) >= 7 and r[0].isdigit()]
+        if not rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({n for r in rows for n, v in zip(names, r[3:7]) if v.lower().startswith("active")})
+        return {"sm_mhz": statistics.median(int(r[0]) for r in rows), "sm_max_mhz": int(rows[0][1]),
+                "power_w_max": max(float(r[2]) for r in rows), "samples": len(rows), "reasons": reasons}
+
+
+# -------------------------------------------------------------------------------------------------
+def cpu_worker(args):
+    """One process of the CPU baseline: the reference's Sample()+Correlate() (oracle/_ref) or the
+    C port (oracle/liboracle.so) over `runs` runs of the bench workload."""
+    sys.path.insert(0, str(ROOT / "oracle"))
+    import oracle
+    bits = np.fromfile(args.cpu_worker, np.uint8)
+    nb = args.cpu_runs * 32
+    off = (args.cpu_index * nb * CHUNK) % max(1, bits.size - nb * CHUNK + 1)
+    data = bits[off: off + nb * CHUNK].tobytes()
+    if args.cpu_kind == "reference":
+        eng = oracle.RefHarness(FC, FS, MAX_FO)
+        backend = eng.fft_backend
+    else:
+        eng = oracle.Oracle(FC, FS, MAX_FO, fft_f64=False)
+        backend = "builtin-f32"
+    eng.search_blocks(data[: 2 * CHUNK])              # warm-up (plans, page-in)
+    t0 = time.perf_counter()
+    eng.search_blocks(data)
+    dt = time.perf_counter() - t0
+    print(json.dumps({"corr": nb * 73, "seconds": dt, "backend": backend}))
+
+
+def usable_cores() -> int:
+    """Host cores this process may actually use: affinity mask, capped by the cgroup CPU quota."""
+    n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    try:
+        quota, period = Path("/sys/fs/cgroup/cpu.max").read_text().split()
+        if quota != "max":
+            n = max(1, min(n, int(float(quota) / float(period))))
+    except Exception:
+        pass
+    return n
+
+
+_CPU_SAMPLE = None
+
+
+def cpu_sample_file() -> str:
+    """The bench workload's synthetic capture (one batch), written once for the CPU workers."""
+    global _CPU_SAMPLE
+    if _CPU_SAMPLE is None:
+        with tempfile.NamedTemporaryFile(suffix=".bin", delete=False) as f:
+            make_batches(1, seed=77)[0].tofile(f)
+            _CPU_SAMPLE = f.name
+    return _CPU_SAMPLE
+
+
+def cpu_baseline(runs_per_core: int, cores: int | None = None):
+    sys.path.insert(0, str(ROOT / "oracle"))
+    import oracle
+    kind = "reference" if oracle.ref_available() else "port"
+    cores = cores or usable_cores()
+    path = cpu_sample_file()
+    env = oracle.mkl_env() if kind == "reference" else dict(os.environ)
+    t0 = time.perf_counter()
+    procs = [subprocess.Popen([sys.executable, __file__, "--cpu-worker", path, "--cpu-kind", kind, "--cpu-runs",
+                               str(runs_per_core), "--cpu-index", str(i)], stdout=subprocess.PIPE, text=True, env=env)
+             for i in range(cores)]
+    res = [json.loads(p.communicate()[0].strip().split("\n")[-1]) for p in procs]
+    wall = time.perf_counter() - t0
+    busy = max(r["seconds"] for r in res)
+    total = sum(r["corr"] for r in res)
+    return {"value": total / busy, "unit": UNIT, "cores": cores, "kind": kind,
+            "sample": f"{runs_per_core} run(s) = {runs_per_core * 32 * 73} correlations per core of the bench workload, "
+                      f"{cores} single-threaded processes of the reference's Sample()+Correlate() "
+                      f"(FFT backend: {res[0]['backend']}); {busy:.1f} s busy, {wall:.1f} s wall incl. start-up",
+            "single_core": res[0]["corr"] / res[0]["seconds"]}, total, busy
+
+
+# -------------------------------------------------------------------------------------------------
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    # size the sample so K timed steps finish in a few minutes: one "step" = runs_per_core runs on every core
+    runs_per_core = 2
+    for _ in range(args.warmup):
+        pass                                   # worker processes warm themselves up (plans, page-in)
+    vals, ms = [], []
+    for _ in range(max(1, args.steps)):
+        cb, total, busy = cpu_baseline(runs_per_core)
+        vals.append(total / busy)
+        ms.append(busy * 1e3)
+    v = statistics.median(vals)
+    os.unlink(cpu_sample_file())
+    line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": statistics.median(ms), "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload_config(args.gpus),
+            "cpu_baseline": {"value": v, "unit": UNIT, "cores": cb["cores"], "kind": cb["kind"], "sample": cb["sample"]},
+            "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line))
+
+
+def run_engine(args, rank, world, local_rank):
+    import torch
+    import gpsacq_loader
+    ga = gpsacq_loader.load()
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    dev = torch.device("cuda", local_rank)
+    torch.cuda.set_device(dev)
+
+    nb = RUNS_PER_STEP * 32
+    batches = make_batches(N_BATCHES, seed=rank + 1)            # every rank searches different runs of the stream
+    acq = ga.Acquisition(FC, FS, MAX_FO, device=local_rank, max_blocks=nb)
+    ndop = acq.n_doppler
+    corr_per_step = nb * ndop
+    d_bits = [torch.from_numpy(b).to(dev) for b in batches]
+    h_bits = [torch.from_numpy(b).pin_memory() for b in batches]
+    d_out = torch.zeros(nb * 32, dtype=torch.uint8, device=dev)
+    d_all = torch.zeros(world * nb * 32, dtype=torch.uint8, device=dev) if world > 1 else None
+    # a non-default stream: libgpsacq launches on it and the CUDA events below are recorded on it
+    stream = torch.cuda.Stream(device=dev)
+    torch.cuda.set_stream(stream)
+    acq.set_stream(stream.cuda_stream)
+
+    def step_device(i):
+        acq.search_blocks_device(d_bits[i % N_BATCHES].data_ptr(), nb, None, d_out.data_ptr())
+        if world > 1:
+            dist.all_gather_into_tensor(d_all, d_out)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    # ---- device-resident timing ------------------------------------------------------------------
+    for i in range(args.warmup):
+        step_device(i)
+    barrier()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    cell_ms = []
+    e0.record(stream)
+    for i in range(args.steps):
+        step_device(i)
+    e1.record(stream)
+    barrier()
+    total_ms = e0.elapsed_time(e1)
+    # per-launch time of the dominant kernel: a second pass with a read-back of the library's events
+    for i in range(min(args.steps, 8)):
+        step_device(i)
+        cell_ms.append(acq.stage_times()["cells_ms"])
+    barrier()
+    clocks = sampler.finish()
+    stage = acq.stage_times()
+
+    # ---- end to end through the host-buffer C-ABI call --------------------------------------------
+    acq.set_stream(None)
+    peaks = None
+    for i in range(min(args.warmup, 3)):
+        peaks = acq.search_blocks(h_bits[i % N_BATCHES].numpy())
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(args.steps):
+        peaks = acq.search_blocks(h_bits[i % N_BATCHES].numpy())
+    torch.cuda.synchronize(dev)
+    e2e_s = time.perf_counter() - t0
+
+    t = torch.tensor([total_ms, e2e_s * 1e3], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    total_ms, e2e_ms = float(t[0]), float(t[1])
+    detected = int((peaks["snr"] >= 25).sum())
+
+    if rank == 0:
+        peaks_file = ROOT / "MEASURED_PEAKS.json"
+        if peaks_file.exists():
+            peak_gbs, peak_src = json.loads(peaks_file.read_text())["hbm_gbs"], "measured (MEASURED_PEAKS.json hbm_gbs)"
+        else:
+            peak_gbs, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
+        bpc = acq.info["bytes_per_corr"]
+        cell_avg_ms = statistics.mean(cell_ms)
+        achieved = corr_per_step * bpc / (cell_avg_ms * 1e-3) / 1e9
+        traffic = None
+        prof = ROOT / "profiles" / "cell_kernel_dram.json"
+        if prof.exists():
+            traffic = json.loads(prof.read_text()).get("dram_bytes_per_launch")
+        value = world * corr_per_step * args.steps / (total_ms * 1e-3)
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": workload_config(world),
+                "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak_gbs, "unit": "GB/s",
+                             "frac": achieved / peak_gbs, "traffic": traffic, "kernel": "cell_kernel",
+                             "launch_ms": cell_avg_ms, "bytes_per_launch": corr_per_step * bpc, "peak_source": peak_src,
+                             "whole_step_frac": value / world * bpc / 1e9 / peak_gbs},
+                "e2e": {"value": world * corr_per_step * args.steps / (e2e_ms * 1e-3), "unit": UNIT,
+                        "h2d_bytes_per_step": nb * CHUNK + nb * 4, "d2h_bytes_per_step": nb * 32,
+                        "ms_per_step": e2e_ms / args.steps},
+                "gpu_launches": ga_launches(args.steps),
+                "clocks": clocks,
+                "stage_ms": {k: round(v, 4) for k, v in stage.items()},
+                "detected_prns_last_step": detected}
+        if world == 1 and not args.no_cpu_baseline:
+            cb, _, _ = cpu_baseline(runs_per_core=4)
+            os.unlink(cpu_sample_file())
+            line["cpu_baseline"] = cb
+        print(json.dumps(line))
+    acq.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def ga_launches(steps: int) -> int:
+    return 3 * steps            # GPSACQ_LAUNCHES_PER_BATCH: fwd_kernel, cell_kernel, best_kernel
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=40)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-worker")
+    ap.add_argument("--cpu-kind", default="reference")
+    ap.add_argument("--cpu-runs", type=int, default=2)
+    ap.add_argument("--cpu-index", type=int, default=0)
+    args = ap.parse_args()
+    if args.cpu_worker:
+        return cpu_worker(args)
+    args.warmup = max(args.warmup, 3)
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        return run_reference(args, rank, world)
+    run_engine(args, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()

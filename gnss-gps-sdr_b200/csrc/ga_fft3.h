@@ -24,16 +24,32 @@
 
 namespace ga {
 
-template <int N1_, int RA_, int RB_, int RC_>
+constexpr int cmax3(int a, int b, int c) { return a > b ? (a > c ? a : c) : (b > c ? b : c); }
+
+// Shared-memory layouts.  A logical element (a,b,c) sits at sa*a + sb*b + sc*c where
+// (sa,sb,sc) is a rotation of the stride set {Q, P, 1} (P, Q odd so that a warp's 64-bit
+// accesses spread over the banks whichever stride is lane-fastest):
+//   ORI 0: (Q,P,1)   ORI 1: (1,Q,P)   ORI 2: (P,1,Q)
+// In orientation k+1 the pass-A pencil of thread t covers exactly the addresses of the
+// pass-C pencil of thread t in orientation k, so with ROT geometries (RA=RB=RC) consecutive
+// sub-sequences alternate orientation and need NO barrier between pass C of one and pass A
+// of the next (the same thread reads, then overwrites, its own 20 words).
+template <int N1_, int RA_, int RB_, int RC_, bool ROT_ = false>
 struct Geom {
     static constexpr int N1 = N1_, RA = RA_, RB = RB_, RC = RC_;
+    static constexpr bool ROT = ROT_;
+    static_assert(!ROT_ || (RA_ == RB_ && RB_ == RC_), "rotating layouts need equal radices");
     static constexpr int N2 = RA * RB * RC, N = N1 * N2;
-    static constexpr int SB = RC | 1;        // odd row pitch: pass-C lanes (stride SB) hit distinct banks
-    static constexpr int SA = RB * SB;
-    static constexpr int SMEM_ELEMS = RA * SA;
+    static constexpr int RMAX = cmax3(RA, RB, RC);
+    static constexpr int P = ROT ? (RMAX | 1) : (RC | 1);
+    static constexpr int Q = ROT ? ((P * RMAX) | 1) : RB * P;
+    static constexpr int SMEM_ELEMS = ROT ? Q * RMAX : RA * Q;
+    static constexpr int NORI = ROT ? 3 : 1;
     static constexpr int NA = RB * RC, NB = RA * RC, NC = RA * RB;   // butterflies per pass
     static constexpr int OUT_STRIDE = RA * RB;                        // tau step between a thread's outputs
-    GA_HD static int addr(int a, int b, int c) { return a * SA + b * SB + c; }
+    template <int ORI> static constexpr int sa() { return ORI == 0 ? Q : ORI == 1 ? 1 : P; }
+    template <int ORI> static constexpr int sb() { return ORI == 0 ? P : ORI == 1 ? Q : 1; }
+    template <int ORI> static constexpr int sc() { return ORI == 0 ? 1 : ORI == 1 ? P : Q; }
 };
 
 template <int DIR> GA_HD cf tw_load(const cf *tw, int idx)
@@ -43,45 +59,48 @@ template <int DIR> GA_HD cf tw_load(const cf *tw, int idx)
 }
 
 // ---- pass A tail: butterfly along a, twiddle, store -----------------------------
-template <class G, int DIR>
+template <class G, int DIR, int ORI = 0>
 GA_HD void passA_finish(cf (&p)[G::RA], int j, int s_tw, const cf *tw, cf *sm)
 {
     Radix<G::RA, DIR>::run(p);
     cf w[G::RA];
     unit_powers<G::RA>(tw_load<DIR>(tw, G::N1 * j + s_tw), w);
     const int b = j / G::RC, c = j - b * G::RC;
-    cf *dst = sm + G::addr(0, b, c);
+    cf *dst = sm + G::template sb<ORI>() * b + G::template sc<ORI>() * c;
     dst[0] = p[0];
     GA_UNROLL
-    for (int u = 1; u < G::RA; u++) dst[u * G::SA] = cmul(p[u], w[u]);
+    for (int u = 1; u < G::RA; u++) dst[u * G::template sa<ORI>()] = cmul(p[u], w[u]);
 }
 
 // ---- pass B: in place along b -----------------------------------------------------
-template <class G, int DIR>
+template <class G, int DIR, int ORI = 0>
 GA_HD void passB(int j2, int s_tw, const cf *tw, cf *sm)
 {
-    const int u = j2 / G::RC, c = j2 - u * G::RC;
-    cf *col = sm + G::addr(u, 0, c);
+    // lane-fastest index = the one with the small stride in this orientation
+    int u, c;
+    if (ORI == 0) { u = j2 / G::RC; c = j2 - u * G::RC; }
+    else          { c = j2 / G::RA; u = j2 - c * G::RA; }
+    cf *col = sm + G::template sa<ORI>() * u + G::template sc<ORI>() * c;
     cf p[G::RB];
     GA_UNROLL
-    for (int b = 0; b < G::RB; b++) p[b] = col[b * G::SB];
+    for (int b = 0; b < G::RB; b++) p[b] = col[b * G::template sb<ORI>()];
     Radix<G::RB, DIR>::run(p);
     cf w[G::RB];
     unit_powers<G::RB>(tw_load<DIR>(tw, (G::N1 * c + s_tw) * G::RA), w);
     col[0] = p[0];
     GA_UNROLL
-    for (int v = 1; v < G::RB; v++) col[v * G::SB] = cmul(p[v], w[v]);
+    for (int v = 1; v < G::RB; v++) col[v * G::template sb<ORI>()] = cmul(p[v], w[v]);
 }
 
 // ---- pass C: along c, results stay in registers ---------------------------------
 // returns tau0 = u + RA*v; p[w] is output tau0 + RA*RB*w
-template <class G, int DIR>
+template <class G, int DIR, int ORI = 0>
 GA_HD int passC(int j3, const cf *sm, cf (&p)[G::RC])
 {
     const int u = j3 / G::RB, v = j3 - u * G::RB;
-    const cf *row = sm + G::addr(u, v, 0);
+    const cf *row = sm + G::template sa<ORI>() * u + G::template sb<ORI>() * v;
     GA_UNROLL
-    for (int c = 0; c < G::RC; c++) p[c] = row[c];
+    for (int c = 0; c < G::RC; c++) p[c] = row[c * G::template sc<ORI>()];
     Radix<G::RC, DIR>::run(p);
     return u + G::RA * v;
 }
@@ -106,7 +125,7 @@ GA_HD void cell_sub_offsets(int s, int dop, int &sp, int &eoff)
 
 // pass A of a cell: thread j of NA.  xs = conj(X) sub-sequence s (N2 values),
 // cs = Cext[sv][sp] + eoff.
-template <class G>
+template <class G, int ORI = 0>
 GA_HD void cell_passA(int j, int s, const cf *xs, const cf *cs, const cf *tw, cf *sm)
 {
     cf p[G::RA];
@@ -115,18 +134,23 @@ GA_HD void cell_passA(int j, int s, const cf *xs, const cf *cs, const cf *tw, cf
         const cf x = ldg(xs + a * G::NA + j), c = ldg(cs + a * G::NA + j);
         p[a] = cmul(x, c);
     }
-    passA_finish<G, +1>(p, j, s, tw, sm);
+    passA_finish<G, +1, ORI>(p, j, s, tw, sm);
 }
 
 // pass C of a cell with accumulation of term s into the thread's outputs.
 // ks = ktab + s*RC, ktab[s*RC+w] = exp(+2*pi*i*s*w/(N1*RC)).
-template <class G, int NW>
+template <class G, int NW, int ORI = 0>
 GA_HD void cell_passC_acc(int j3, const cf *sm, const cf *ks, cf (&acc)[NW])
 {
     cf p[G::RC];
-    passC<G, +1>(j3, sm, p);
+    passC<G, +1, ORI>(j3, sm, p);
+#ifdef GA_EXPERIMENT_FEWACC   // timing experiment only (wrong results): 2 accumulators instead of NW
+    GA_UNROLL
+    for (int w = 0; w < NW; w++) cfma(acc[w & 1], p[w], ks[w]);
+#else
     GA_UNROLL
     for (int w = 0; w < NW; w++) cfma(acc[w], p[w], ks[w]);
+#endif
 }
 
 // peak/sum over one thread's outputs (c/search_offline.cpp:190-194): power,

@@ -14,6 +14,7 @@
 // pointer offset.
 #pragma once
 #include <cuda_runtime.h>
+#include <stdint.h>
 #include "ga_fft3.h"
 
 namespace ga {
@@ -215,6 +216,363 @@ __global__ void __launch_bounds__(T, MINB) cell_kernel(const cf *__restrict__ xd
             }
         }
         // red_* are rewritten only after the next cell's __syncthreads()s: no extra barrier needed
+    }
+}
+
+// ---------------------------------------------------------------------------------
+// Tensor-memory variant of the hot kernel: the per-thread output accumulators (NW complex
+// values per butterfly, 56 floats per thread for 5 x 20^3) live in Blackwell TMEM instead of
+// registers.  TMEM is 128 lanes x 512 columns x 32 bit per SM; with the 32x32b access shape
+// thread i of warp w owns lane 32*(w%4)+i, so a column range is private per-thread storage:
+// tcgen05.ld / tcgen05.st (SASS LDTM / STTM) move it to and from registers.  No tensor-core
+// math is involved -- TMEM is used as a 2nd register file so that the radix-20 butterflies
+// keep the whole 128-register budget (no local-memory spills, which the register version pays
+// with ~150 M L2 write sectors per launch).
+// ---------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+template <int N> struct TmVec;   // N 32-bit columns per thread
+template <> struct TmVec<2> {
+    static __device__ __forceinline__ void ld(uint32_t a, float *v)
+    {
+        uint32_t r0, r1;
+        asm volatile("tcgen05.ld.sync.aligned.32x32b.x2.b32 {%0,%1}, [%2];" : "=r"(r0), "=r"(r1) : "r"(a) : "memory");
+        v[0] = __uint_as_float(r0); v[1] = __uint_as_float(r1);
+    }
+    static __device__ __forceinline__ void st(uint32_t a, const float *v)
+    {
+        asm volatile("tcgen05.st.sync.aligned.32x32b.x2.b32 [%0], {%1,%2};" ::"r"(a), "r"(__float_as_uint(v[0])), "r"(__float_as_uint(v[1])) : "memory");
+    }
+};
+template <> struct TmVec<4> {
+    static __device__ __forceinline__ void ld(uint32_t a, float *v)
+    {
+        uint32_t r0, r1, r2, r3;
+        asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(a) : "memory");
+        v[0] = __uint_as_float(r0); v[1] = __uint_as_float(r1); v[2] = __uint_as_float(r2); v[3] = __uint_as_float(r3);
+    }
+    static __device__ __forceinline__ void st(uint32_t a, const float *v)
+    {
+        asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1,%2,%3,%4};" ::"r"(a), "r"(__float_as_uint(v[0])), "r"(__float_as_uint(v[1])),
+                     "r"(__float_as_uint(v[2])), "r"(__float_as_uint(v[3])) : "memory");
+    }
+};
+template <> struct TmVec<8> {
+    static __device__ __forceinline__ void ld(uint32_t a, float *v)
+    {
+        uint32_t r[8];
+        asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                     : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]) : "r"(a) : "memory");
+#pragma unroll
+        for (int i = 0; i < 8; i++) v[i] = __uint_as_float(r[i]);
+    }
+    static __device__ __forceinline__ void st(uint32_t a, const float *v)
+    {
+        asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"r"(a), "r"(__float_as_uint(v[0])),
+                     "r"(__float_as_uint(v[1])), "r"(__float_as_uint(v[2])), "r"(__float_as_uint(v[3])), "r"(__float_as_uint(v[4])),
+                     "r"(__float_as_uint(v[5])), "r"(__float_as_uint(v[6])), "r"(__float_as_uint(v[7])) : "memory");
+    }
+};
+// move NF floats (NF even) between registers and consecutive TMEM columns in x8/x4/x2 pieces
+template <int NF, bool LOAD> __device__ __forceinline__ void tm_move(uint32_t a, float *v)
+{
+    if constexpr (NF >= 8) { if (LOAD) TmVec<8>::ld(a, v); else TmVec<8>::st(a, v); tm_move<NF - 8, LOAD>(a + 8, v + 8); }
+    else if constexpr (NF >= 4) { if (LOAD) TmVec<4>::ld(a, v); else TmVec<4>::st(a, v); tm_move<NF - 4, LOAD>(a + 4, v + 4); }
+    else if constexpr (NF >= 2) { if (LOAD) TmVec<2>::ld(a, v); else TmVec<2>::st(a, v); tm_move<NF - 2, LOAD>(a + 2, v + 2); }
+}
+constexpr uint32_t pow2_at_least(uint32_t x, uint32_t p = 32) { return p >= x ? p : pow2_at_least(x, p * 2); }
+
+template <class G, int T, int NW, int GID>
+__global__ void __launch_bounds__(T, 2) cell_kernel_tm(const cf *__restrict__ xd, const cf *__restrict__ cext,
+                                                       const int *__restrict__ sv_of_block, const cf *__restrict__ tw,
+                                                       int n_cells, int n_dop, int dmax, int wlen, CellStat *__restrict__ cells)
+{
+    static_assert(T % 32 == 0, "tcgen05.ld/st are warp-collective: whole warps only");
+    constexpr int ITA = cdiv(G::NA, T), ITB = cdiv(G::NB, T), ITC = cdiv(G::NC, T);
+    constexpr int NWARP = T / 32;
+    constexpr uint32_t COLS_THREAD = ITC * 2 * NW;                 // accumulator floats per thread
+    constexpr uint32_t COL_SLOT = (COLS_THREAD + 7u) & ~7u;        // column range of one warp "row" (4 warps share the lanes)
+    constexpr uint32_t TM_COLS = pow2_at_least(COL_SLOT * cdiv(NWARP, 4));
+    static_assert(TM_COLS <= 256, "two CTAs per SM must fit in the 512 TMEM columns");
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    cf *sm = reinterpret_cast<cf *>(smem_raw);
+    __shared__ float red_best[NWARP], red_sum[NWARP];
+    __shared__ int red_idx[NWARP];
+    __shared__ uint32_t tm_base_s;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+
+    if (wid == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tm_base_s)), "r"(TM_COLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tm_base = tm_base_s;
+    // this warp's private window: lanes 32*(wid%4).., columns (wid/4)*COL_SLOT..
+    const uint32_t tm_mine = tm_base + ((32u * (uint32_t)(wid & 3)) << 16) + (uint32_t)(wid >> 2) * COL_SLOT;
+
+    for (int cell = blockIdx.x; cell < n_cells; cell += gridDim.x) {
+        const int blk = cell / n_dop, dop = cell - blk * n_dop - dmax;
+        const int sv = sv_of_block ? sv_of_block[blk] : (blk & 31);
+        const cf *xb = xd + (size_t)blk * G::N;
+        const cf *cb = cext + (size_t)sv * (2 * G::N);
+        float best = 0.0f, sum = 0.0f;
+        int besti = 0;
+
+        for (int s = 0; s < G::N1; s++) {
+            int sp, eoff;
+            cell_sub_offsets<G>(s, dop, sp, eoff);
+            const cf *xs = xb + (size_t)s * G::N2;
+            const cf *cs = cb + (size_t)sp * (2 * G::N2) + eoff;
+#pragma unroll
+            for (int it = 0; it < ITA; it++) {
+                const int j = tid + it * T;
+                if (ITA * T == G::NA || j < G::NA) cell_passA<G>(j, s, xs, cs, tw, sm);
+            }
+            __syncthreads();
+#pragma unroll
+            for (int it = 0; it < ITB; it++) {
+                const int j = tid + it * T;
+                if (ITB * T == G::NB || j < G::NB) passB<G, +1>(j, s, tw, sm);
+            }
+            __syncthreads();
+            const cf *ks = c_ktab[GID] + s * G::RC;
+#pragma unroll
+            for (int it = 0; it < ITC; it++) {
+                // every lane runs the butterfly (out-of-range lanes redo the last one) so that the
+                // warp-collective TMEM accesses below are never under divergence
+                const int j = tid + it * T;
+                const bool act = (ITC * T == G::NC) || j < G::NC;
+                const int jc = act ? j : G::NC - 1;
+                cf p[G::RC];
+                const int tau0 = passC<G, +1>(jc, sm, p);
+                float a[2 * NW];
+                const uint32_t col = tm_mine + (uint32_t)(it * 2 * NW);
+                if (s == 0) {
+#pragma unroll
+                    for (int w = 0; w < NW; w++) { a[2 * w] = p[w].x; a[2 * w + 1] = p[w].y; }   // ktab[0][w] = 1
+                } else {
+                    tm_move<2 * NW, true>(col, a);
+                    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+                    for (int w = 0; w < NW; w++) {
+                        cf t = mk(a[2 * w], a[2 * w + 1]);
+                        cfma(t, p[w], ks[w]);
+                        a[2 * w] = t.x; a[2 * w + 1] = t.y;
+                    }
+                }
+                if (s < G::N1 - 1) {
+                    tm_move<2 * NW, false>(col, a);
+                } else if (act) {
+                    // last sub-sequence: the outputs are complete -> power, first max, sum (:190-194)
+#pragma unroll
+                    for (int w = 0; w < NW; w++) {
+                        const int tau = tau0 + G::OUT_STRIDE * w;
+                        if (tau < wlen) {
+                            const float pwr = fmaf(a[2 * w], a[2 * w], a[2 * w + 1] * a[2 * w + 1]);
+                            if (pwr > best || (pwr == best && tau < besti)) { best = pwr; besti = tau; }
+                            sum += pwr;
+                        }
+                    }
+                }
+            }
+            asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+            __syncthreads();      // smem is rewritten by the next sub-sequence's pass A
+        }
+
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) {
+            const float ob = __shfl_down_sync(0xffffffffu, best, off);
+            const int oi = __shfl_down_sync(0xffffffffu, besti, off);
+            const float os = __shfl_down_sync(0xffffffffu, sum, off);
+            if (ob > best || (ob == best && oi < besti)) { best = ob; besti = oi; }
+            sum += os;
+        }
+        if (lane == 0) { red_best[wid] = best; red_idx[wid] = besti; red_sum[wid] = sum; }
+        __syncthreads();
+        if (wid == 0) {
+            best = lane < NWARP ? red_best[lane] : 0.0f;
+            besti = lane < NWARP ? red_idx[lane] : 0x7fffffff;
+            sum = lane < NWARP ? red_sum[lane] : 0.0f;
+#pragma unroll
+            for (int off = 16; off > 0; off >>= 1) {
+                const float ob = __shfl_down_sync(0xffffffffu, best, off);
+                const int oi = __shfl_down_sync(0xffffffffu, besti, off);
+                const float os = __shfl_down_sync(0xffffffffu, sum, off);
+                if (ob > best || (ob == best && oi < besti)) { best = ob; besti = oi; }
+                sum += os;
+            }
+            if (lane == 0) {
+                CellStat r; r.max_pwr = best; r.tot_pwr = sum; r.max_idx = besti; r.pad = 0;
+                cells[cell] = r;
+            }
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (wid == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tm_base), "r"(TM_COLS) : "memory");
+}
+
+// ---------------------------------------------------------------------------------
+// Rotating-layout variant of the hot kernel (geometries with RA=RB=RC, e.g. 5 x 20^3).
+// Consecutive sub-sequences use shared-memory orientations 0,1,2,0,... (ga_fft3.h): the
+// pass-A pencil a thread writes for sub-sequence g+1 is the pass-C pencil it has just read
+// for sub-sequence g, so only TWO barriers per sub-sequence remain (before and after pass
+// B) and the operand loads of the next sub-sequence are free to overlap pass C.
+// The orientation keeps rotating across cells, so there is no barrier between cells either.
+// ---------------------------------------------------------------------------------
+template <class G, int T, int NW>
+struct CellState {
+    static constexpr int ITC = cdiv(G::NC, T);
+    cf acc[ITC][NW];
+    const cf *xb, *cb;
+    int dop, cell;
+};
+
+template <class G, int T, int NW, int GID, int ORI>
+__device__ __forceinline__ bool cell_rot_step(CellState<G, T, NW> &st, int s, cf *sm, const cf *__restrict__ xd,
+                                              const cf *__restrict__ cext, const int *__restrict__ sv_of_block,
+                                              const cf *__restrict__ tw, int n_cells, int n_dop, int dmax, int wlen,
+                                              CellStat *__restrict__ cells, float *red_best, float *red_sum, int *red_idx)
+{
+    constexpr int ITA = cdiv(G::NA, T), ITB = cdiv(G::NB, T), ITC = cdiv(G::NC, T);
+    constexpr int NWARP = cdiv(T, 32);
+    constexpr int NORI = (ORI + 1) % 3;
+    static_assert(ITA == ITC && G::NA == G::NC, "pass A and pass C must share the thread map");
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+
+    __syncthreads();
+#pragma unroll
+    for (int it = 0; it < ITB; it++) {
+        const int j = tid + it * T;
+        if (ITB * T == G::NB || j < G::NB) passB<G, +1, ORI>(j, s, tw, sm);
+    }
+    __syncthreads();
+    const cf *ks = c_ktab[GID] + s * G::RC;
+#pragma unroll
+    for (int it = 0; it < ITC; it++) {
+        const int j = tid + it * T;
+        if (ITC * T == G::NC || j < G::NC) cell_passC_acc<G, NW, ORI>(j, sm, ks, st.acc[it]);
+    }
+
+    int s_next = s + 1;
+    if (s == G::N1 - 1) {
+        // ---- the cell is complete: |.|^2, first-max / sum, reduce, write the record --------
+        float best = 0.0f, sum = 0.0f;
+        int besti = 0;
+#pragma unroll
+        for (int it = 0; it < ITC; it++) {
+            const int j = tid + it * T;
+            if (ITC * T == G::NC || j < G::NC) {
+                const int u = j / G::RB, v = j - u * G::RB;
+                cell_peak_thread<G, NW>(st.acc[it], u + G::RA * v, wlen, best, besti, sum);
+            }
+        }
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) {
+            const float ob = __shfl_down_sync(0xffffffffu, best, off);
+            const int oi = __shfl_down_sync(0xffffffffu, besti, off);
+            const float os = __shfl_down_sync(0xffffffffu, sum, off);
+            if (ob > best || (ob == best && oi < besti)) { best = ob; besti = oi; }
+            sum += os;
+        }
+        if (lane == 0) { red_best[wid] = best; red_idx[wid] = besti; red_sum[wid] = sum; }
+        __syncthreads();
+        if (wid == 0) {
+            best = lane < NWARP ? red_best[lane] : 0.0f;
+            besti = lane < NWARP ? red_idx[lane] : 0x7fffffff;
+            sum = lane < NWARP ? red_sum[lane] : 0.0f;
+#pragma unroll
+            for (int off = 16; off > 0; off >>= 1) {
+                const float ob = __shfl_down_sync(0xffffffffu, best, off);
+                const int oi = __shfl_down_sync(0xffffffffu, besti, off);
+                const float os = __shfl_down_sync(0xffffffffu, sum, off);
+                if (ob > best || (ob == best && oi < besti)) { best = ob; besti = oi; }
+                sum += os;
+            }
+            if (lane == 0) {
+                CellStat r; r.max_pwr = best; r.tot_pwr = sum; r.max_idx = besti; r.pad = 0;
+                cells[st.cell] = r;
+            }
+        }
+        // ---- next cell of this persistent CTA -------------------------------------------------
+        st.cell += gridDim.x;
+        if (st.cell >= n_cells) return false;
+        const int blk = st.cell / n_dop;
+        st.dop = st.cell - blk * n_dop - dmax;
+        const int sv = sv_of_block ? sv_of_block[blk] : (blk & 31);
+        st.xb = xd + (size_t)blk * G::N;
+        st.cb = cext + (size_t)sv * (2 * G::N);
+#pragma unroll
+        for (int it = 0; it < ITC; it++)
+#pragma unroll
+            for (int w = 0; w < NW; w++) st.acc[it][w] = mk(0.0f, 0.0f);
+        s_next = 0;
+    }
+    // ---- pass A of the next sub-sequence, into the rows this thread has just consumed ---------
+    int sp, eoff;
+    cell_sub_offsets<G>(s_next, st.dop, sp, eoff);
+    const cf *xs = st.xb + (size_t)s_next * G::N2;
+    const cf *cs = st.cb + (size_t)sp * (2 * G::N2) + eoff;
+#pragma unroll
+    for (int it = 0; it < ITA; it++) {
+        const int j = tid + it * T;
+        if (ITA * T == G::NA || j < G::NA) cell_passA<G, NORI>(j, s_next, xs, cs, tw, sm);
+    }
+    return true;
+}
+
+template <class G, int T, int NW, int MAXREG, int GID>
+__global__ void __launch_bounds__(T) __maxnreg__(MAXREG)
+cell_kernel_rot(const cf *__restrict__ xd, const cf *__restrict__ cext, const int *__restrict__ sv_of_block,
+                const cf *__restrict__ tw, int n_cells, int n_dop, int dmax, int wlen, CellStat *__restrict__ cells)
+{
+    static_assert(G::ROT, "rotating-layout geometry required");
+    constexpr int ITA = cdiv(G::NA, T), ITC = cdiv(G::NC, T);
+    constexpr int NWARP = cdiv(T, 32);
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    cf *sm = reinterpret_cast<cf *>(smem_raw);
+    __shared__ float red_best[NWARP], red_sum[NWARP];
+    __shared__ int red_idx[NWARP];
+    const int tid = threadIdx.x;
+
+    CellState<G, T, NW> st;
+    st.cell = blockIdx.x;
+    if (st.cell >= n_cells) return;
+    {
+        const int blk = st.cell / n_dop;
+        st.dop = st.cell - blk * n_dop - dmax;
+        const int sv = sv_of_block ? sv_of_block[blk] : (blk & 31);
+        st.xb = xd + (size_t)blk * G::N;
+        st.cb = cext + (size_t)sv * (2 * G::N);
+    }
+#pragma unroll
+    for (int it = 0; it < ITC; it++)
+#pragma unroll
+        for (int w = 0; w < NW; w++) st.acc[it][w] = mk(0.0f, 0.0f);
+    {
+        int sp, eoff;
+        cell_sub_offsets<G>(0, st.dop, sp, eoff);
+        const cf *cs = st.cb + (size_t)sp * (2 * G::N2) + eoff;
+#pragma unroll
+        for (int it = 0; it < ITA; it++) {
+            const int j = tid + it * T;
+            if (ITA * T == G::NA || j < G::NA) cell_passA<G, 0>(j, 0, st.xb, cs, tw, sm);
+        }
+    }
+    int s = 0, ori = 0;
+    for (;;) {
+        bool more;
+        if (ori == 0)
+            more = cell_rot_step<G, T, NW, GID, 0>(st, s, sm, xd, cext, sv_of_block, tw, n_cells, n_dop, dmax, wlen, cells, red_best, red_sum, red_idx);
+        else if (ori == 1)
+            more = cell_rot_step<G, T, NW, GID, 1>(st, s, sm, xd, cext, sv_of_block, tw, n_cells, n_dop, dmax, wlen, cells, red_best, red_sum, red_idx);
+        else
+            more = cell_rot_step<G, T, NW, GID, 2>(st, s, sm, xd, cext, sv_of_block, tw, n_cells, n_dop, dmax, wlen, cells, red_best, red_sum, red_idx);
+        if (!more) break;
+        s = (s + 1 == G::N1) ? 0 : s + 1;
+        ori = (ori + 1 == 3) ? 0 : ori + 1;
     }
 }
 

@@ -24,13 +24,18 @@ static_assert(sizeof(gpsacq_cell) == sizeof(CellStat) && sizeof(gpsacq_cell) == 
 
 // ---- geometries: N = 40000 = N1 * (RA*RB*RC), N2 >= W --------------------------------
 typedef Geom<10, 20, 20, 10> G4000;    // W <= 4000   (FS <= 4 MHz, e.g. rtl-sdr 2.8 MHz)
-typedef Geom<5, 20, 20, 20> G8000;     // W <= 8000   (FS <= 8 MHz, e.g. 5.456 MHz)
+#ifndef GA_G8000_ROT
+#define GA_G8000_ROT 0
+#endif
+typedef Geom<5, 20, 20, 20, GA_G8000_ROT != 0> G8000;  // W <= 8000 (FS <= 8 MHz, e.g. 5.456 MHz); rotating smem layouts
 typedef Geom<4, 25, 20, 20> G10000;    // W <= 10000  (FS <= 10 MHz, e.g. 8.184 MHz, 10 MHz)
 enum { GID_4000 = 0, GID_8000 = 1, GID_10000 = 2 };
 
-#define CELL_T_4000 200
-#define CELL_T_8000 200
-#define CELL_T_10000 250
+#define CELL_T_4000 224
+#ifndef CELL_T_8000
+#define CELL_T_8000 224     // 7 whole warps (tcgen05.ld/st are warp-collective); 400 butterflies per pass
+#endif
+#define CELL_T_10000 256
 #define FWD_T 256
 
 static const double kCPS = 1.023e6;    // chip rate, c/gps_offline.h:30
@@ -82,12 +87,32 @@ struct gpsacq {
     } while (0)
 
 // ---- kernel dispatch ------------------------------------------------------------------
+#ifndef CELL_MINB
+#define CELL_MINB 2
+#endif
+#ifndef CELL_MAXREG
+#define CELL_MAXREG 144      // 2 CTAs x 7 warps x 32 lanes x 144 regs <= 64K registers per SM
+#endif
+
+#ifndef GA_CELL_TMEM
+#define GA_CELL_TMEM 1       // accumulators in tensor memory (cell_kernel_tm); 0 = registers (cell_kernel)
+#endif
+
+template <class G, int T, int NW, int GID> struct CellKernel {
+    static auto get()
+    {
+        if constexpr (G::ROT) return cell_kernel_rot<G, T, NW, CELL_MAXREG, GID>;   // experimental 2-barrier kernel
+        else if constexpr (GA_CELL_TMEM != 0 && T % 32 == 0) return cell_kernel_tm<G, T, NW, GID>;
+        else return cell_kernel<G, T, NW, CELL_MINB, GID>;
+    }
+};
+
 template <class G, int T, int NW, int GID>
 static int launch_cells_t(gpsacq *h, size_t n_blocks, const int *d_sv)
 {
     const int n_cells = (int)(n_blocks * (size_t)h->ndop);
     const int grid = std::min(n_cells, h->cell_ctas);
-    cell_kernel<G, T, NW, 2, GID><<<grid, T, h->cell_smem, h->stream>>>(
+    CellKernel<G, T, NW, GID>::get()<<<grid, T, h->cell_smem, h->stream>>>(
         h->d_xd, h->d_cext, d_sv, h->d_tw, n_cells, h->ndop, h->dmax, h->w, h->d_cells);
     CUDA_TRY(h, cudaGetLastError());
     return 0;
@@ -96,19 +121,24 @@ static int launch_cells_t(gpsacq *h, size_t n_blocks, const int *d_sv)
 template <class G, int T, int NW, int GID>
 static int setup_cells_t(gpsacq *h)
 {
-    auto kern = cell_kernel<G, T, NW, 2, GID>;
+    auto kern = CellKernel<G, T, NW, GID>::get();
     h->cell_smem = (int)(G::SMEM_ELEMS * sizeof(cf));
     h->cell_threads = T;
     h->cell_nw = NW;
     CUDA_TRY(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, h->cell_smem));
     // ask for a shared-memory carveout that fits two CTAs (the rest stays L1 for the operand loads)
-    const int want = 2 * (h->cell_smem + 2048);
+    const int want = CELL_MINB * (h->cell_smem + 2048);
     int pct = (int)((want * 100LL + 228 * 1024 - 1) / (228 * 1024));
     if (pct > 100) pct = 100;
     CUDA_TRY(h, cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, pct));
     int per_sm = 0;
     CUDA_TRY(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, T, h->cell_smem));
     if (per_sm < 1) { h->err = "cell kernel does not fit on an SM"; return GPSACQ_ECUDA; }
+    // The occupancy query is conservative for kernels that allocate tensor memory (it cannot see the
+    // column count, a run-time operand of tcgen05.alloc, and reports one CTA per SM).  Registers and
+    // shared memory are sized for CELL_MINB CTAs (__launch_bounds__, carveout above) and each CTA
+    // allocates at most 256 of the 512 TMEM columns, so CELL_MINB CTAs are resident.
+    if (GA_CELL_TMEM != 0 && !G::ROT && T % 32 == 0 && per_sm < CELL_MINB) per_sm = CELL_MINB;
     h->cell_ctas = per_sm * h->sm_count;
     return 0;
 }

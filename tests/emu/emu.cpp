@@ -13,6 +13,26 @@
 
 using namespace ga;
 
+template <class G, int ORI>
+static void emu_cell_sub(int s, int s_next, const cf *xd_blk, const cf *cext_sv, int dop, const cf *tw, const cf *ktab,
+                         cf *sm, cf *acc)
+{
+    // what cell_rot_step<ORI> does between its barriers, thread by thread
+    constexpr int NW = G::RC;
+    constexpr int NORI = (ORI + 1) % 3;
+    for (int j = 0; j < G::NB; j++) passB<G, +1, ORI>(j, s, tw, sm);
+    int sp = 0, eoff = 0;
+    if (s_next >= 0) cell_sub_offsets<G>(s_next, dop, sp, eoff);
+    for (int j = 0; j < G::NC; j++) {          // pass C then, with NO barrier, pass A of the next sub-sequence
+        cf a[NW];
+        memcpy(a, &acc[(size_t)j * NW], sizeof a);
+        cell_passC_acc<G, NW, ORI>(j, sm, ktab + (size_t)s * G::RC, a);
+        memcpy(&acc[(size_t)j * NW], a, sizeof a);
+        if (s_next >= 0)
+            cell_passA<G, NORI>(j, s_next, xd_blk + (size_t)s_next * G::N2, cext_sv + (size_t)sp * 2 * G::N2 + eoff, tw, sm);
+    }
+}
+
 template <class G>
 static void emu_cell_t(const cf *xd_blk, const cf *cext_sv, int dop, int wlen, cf *y, float *best, int *besti, float *sum)
 {
@@ -20,18 +40,32 @@ static void emu_cell_t(const cf *xd_blk, const cf *cext_sv, int dop, int wlen, c
     std::vector<cf> tw = make_tw(G::N), ktab = make_ktab<G>();
     std::vector<cf> sm((size_t)G::SMEM_ELEMS);
     std::vector<cf> acc((size_t)G::NC * NW, mk(0, 0));
-    for (int s = 0; s < G::N1; s++) {
+    if constexpr (G::ROT) {
         int sp, eoff;
-        cell_sub_offsets<G>(s, dop, sp, eoff);
-        const cf *xs = xd_blk + (size_t)s * G::N2;
-        const cf *cs = cext_sv + (size_t)sp * 2 * G::N2 + eoff;
-        for (int j = 0; j < G::NA; j++) cell_passA<G>(j, s, xs, cs, tw.data(), sm.data());
-        for (int j = 0; j < G::NB; j++) passB<G, +1>(j, s, tw.data(), sm.data());
-        for (int j = 0; j < G::NC; j++) {
-            cf a[NW];
-            memcpy(a, &acc[(size_t)j * NW], sizeof a);
-            cell_passC_acc<G, NW>(j, sm.data(), ktab.data() + (size_t)s * G::RC, a);
-            memcpy(&acc[(size_t)j * NW], a, sizeof a);
+        cell_sub_offsets<G>(0, dop, sp, eoff);
+        for (int j = 0; j < G::NA; j++) cell_passA<G, 0>(j, 0, xd_blk, cext_sv + (size_t)sp * 2 * G::N2 + eoff, tw.data(), sm.data());
+        for (int s = 0; s < G::N1; s++) {
+            const int nxt = s + 1 < G::N1 ? s + 1 : -1;
+            switch (s % 3) {
+            case 0: emu_cell_sub<G, 0>(s, nxt, xd_blk, cext_sv, dop, tw.data(), ktab.data(), sm.data(), acc.data()); break;
+            case 1: emu_cell_sub<G, 1>(s, nxt, xd_blk, cext_sv, dop, tw.data(), ktab.data(), sm.data(), acc.data()); break;
+            default: emu_cell_sub<G, 2>(s, nxt, xd_blk, cext_sv, dop, tw.data(), ktab.data(), sm.data(), acc.data()); break;
+            }
+        }
+    } else {
+        for (int s = 0; s < G::N1; s++) {
+            int sp, eoff;
+            cell_sub_offsets<G>(s, dop, sp, eoff);
+            const cf *xs = xd_blk + (size_t)s * G::N2;
+            const cf *cs = cext_sv + (size_t)sp * 2 * G::N2 + eoff;
+            for (int j = 0; j < G::NA; j++) cell_passA<G>(j, s, xs, cs, tw.data(), sm.data());
+            for (int j = 0; j < G::NB; j++) passB<G, +1>(j, s, tw.data(), sm.data());
+            for (int j = 0; j < G::NC; j++) {
+                cf a[NW];
+                memcpy(a, &acc[(size_t)j * NW], sizeof a);
+                cell_passC_acc<G, NW>(j, sm.data(), ktab.data() + (size_t)s * G::RC, a);
+                memcpy(&acc[(size_t)j * NW], a, sizeof a);
+            }
         }
     }
     float b = 0, sm_ = 0; int bi = 0;
@@ -62,7 +96,7 @@ static void emu_fwd_t(const cf *x, int s, cf *out)
     }
 }
 
-typedef Geom<5, 20, 20, 20> G8000;
+typedef Geom<5, 20, 20, 20, true> G8000;
 typedef Geom<4, 25, 20, 20> G10000;
 typedef Geom<10, 20, 20, 10> G4000;
 
