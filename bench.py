@@ -71,34 +71,50 @@ def workload_config(n_gpus: int):
 
 # -------------------------------------------------------------------------------------------------
 class ClockSampler(threading.Thread):
-    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
-         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-         "clocks_event_reasons.sw_power_cap")
+    """Samples SM clock, power and throttle reasons of one GPU DURING the timed region (NVML, ~2 ms period;
+    falls back to polling nvidia-smi)."""
+    BAD = {"hw_slowdown": 0x8, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20, "sw_power_cap": 0x4}
 
     def __init__(self, index: int):
         super().__init__(daemon=True)
         self.index, self.rows, self._halt = index, [], threading.Event()
+        self.nv = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
 
     def run(self):
         while not self._halt.is_set():
             try:
-                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                      "-i", str(self.index)], capture_output=True, text=True, timeout=5).stdout
-                self.rows.append([c.strip() for c in out.strip().split(",")])
+                if self.nv is not None:
+                    nv = self.nv
+                    self.rows.append((nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM),
+                                      nv.nvmlDeviceGetPowerUsage(self.h) / 1000.0,
+                                      nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)))
+                    self._halt.wait(0.002)
+                else:
+                    out = subprocess.run(["nvidia-smi", "--query-gpu=clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active",
+                                          "--format=csv,noheader,nounits", "-i", str(self.index)],
+                                         capture_output=True, text=True, timeout=5).stdout.strip().split(",")
+                    self.max_mhz = int(out[1])
+                    self.rows.append((int(out[0]), float(out[2]), int(out[3], 16)))
+                    self._halt.wait(0.05)
             except Exception:
-                pass
-            self._halt.wait(0.1)
+                self._halt.wait(0.05)
 
     def finish(self):
         self._halt.set()
         self.join(timeout=6)
-        rows = [r for r in self.rows if len(r) >= 7 and r[0].isdigit()]
-        if not rows:
+        if not self.rows:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = sorted({n for r in rows for n, v in zip(names, r[3:7]) if v.lower().startswith("active")})
-        return {"sm_mhz": statistics.median(int(r[0]) for r in rows), "sm_max_mhz": int(rows[0][1]),
-                "power_w_max": max(float(r[2]) for r in rows), "samples": len(rows), "reasons": reasons}
+        reasons = sorted(n for n, bit in self.BAD.items() if any(r[2] & bit for r in self.rows))
+        return {"sm_mhz": statistics.median(r[0] for r in self.rows), "sm_max_mhz": self.max_mhz,
+                "power_w_max": max(r[1] for r in self.rows), "samples": len(self.rows), "reasons": reasons}
 
 
 # -------------------------------------------------------------------------------------------------

@@ -29,20 +29,44 @@ struct alignas(8) cf { float x, y; };
 #endif
 
 GA_HD cf mk(float x, float y) { cf r; r.x = x; r.y = y; return r; }
+
+// Complex arithmetic on (re, im) pairs.  On sm_100a every operation below is written with the
+// packed FP32x2 intrinsics (__fadd2_rn / __fmul2_rn / __ffma2_rn -> SASS FADD2 / FMUL2 / FFMA2,
+// new on Blackwell): one issue slot does both components, the half-swap and the sign flip of a
+// multiplication by +-i are operand modifiers (.LO_HI, .NP), so a complex add/sub -- with or
+// without a factor i -- is ONE instruction and a complex multiply TWO.  The host build (CPU
+// replay in tests/emu) uses the plain scalar formulas.
+#if defined(__CUDA_ARCH__) && (__CUDA_ARCH__ >= 1000)
+#define GA_PACKED 1
+GA_HD cf cadd(cf a, cf b) { return __fadd2_rn(a, b); }
+GA_HD cf csub(cf a, cf b) { return __fadd2_rn(a, mk(-b.x, -b.y)); }
+GA_HD cf cmul(cf a, cf b) { return __ffma2_rn(mk(a.y, a.x), mk(-b.y, b.y), __fmul2_rn(a, mk(b.x, b.x))); }
+GA_HD cf csqr(cf a) { return cmul(a, a); }
+GA_HD cf cscale(cf a, float s) { return __fmul2_rn(a, mk(s, s)); }
+// acc + a*s  (s real)
+GA_HD cf caxpy(cf acc, cf a, float s) { return __ffma2_rn(a, mk(s, s), acc); }
+// a + DIR*i*b   and   a - DIR*i*b
+template <int DIR> GA_HD cf cadd_i(cf a, cf b) { return DIR > 0 ? __fadd2_rn(a, mk(-b.y, b.x)) : __fadd2_rn(a, mk(b.y, -b.x)); }
+template <int DIR> GA_HD cf csub_i(cf a, cf b) { return DIR > 0 ? __fadd2_rn(a, mk(b.y, -b.x)) : __fadd2_rn(a, mk(-b.y, b.x)); }
+// acc += a*b
+GA_HD void cfma(cf &acc, cf a, cf b) { acc = __ffma2_rn(mk(a.y, a.x), mk(-b.y, b.y), __ffma2_rn(a, mk(b.x, b.x), acc)); }
+#else
+#define GA_PACKED 0
 GA_HD cf cadd(cf a, cf b) { return mk(a.x + b.x, a.y + b.y); }
 GA_HD cf csub(cf a, cf b) { return mk(a.x - b.x, a.y - b.y); }
 GA_HD cf cmul(cf a, cf b) { return mk(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x); }
 GA_HD cf csqr(cf a) { return mk(a.x * a.x - a.y * a.y, 2.0f * a.x * a.y); }
-GA_HD cf cconj(cf a) { return mk(a.x, -a.y); }
 GA_HD cf cscale(cf a, float s) { return mk(a.x * s, a.y * s); }
-// multiply by DIR*i  (DIR=+1: i*a ; DIR=-1: -i*a)
-template <int DIR> GA_HD cf cmul_i(cf a) { return DIR > 0 ? mk(-a.y, a.x) : mk(a.y, -a.x); }
-// acc += a*b
+GA_HD cf caxpy(cf acc, cf a, float s) { return mk(fmaf(a.x, s, acc.x), fmaf(a.y, s, acc.y)); }
+template <int DIR> GA_HD cf cadd_i(cf a, cf b) { return DIR > 0 ? mk(a.x - b.y, a.y + b.x) : mk(a.x + b.y, a.y - b.x); }
+template <int DIR> GA_HD cf csub_i(cf a, cf b) { return DIR > 0 ? mk(a.x + b.y, a.y - b.x) : mk(a.x - b.y, a.y + b.x); }
 GA_HD void cfma(cf &acc, cf a, cf b)
 {
     acc.x = fmaf(a.x, b.x, acc.x); acc.x = fmaf(-a.y, b.y, acc.x);
     acc.y = fmaf(a.x, b.y, acc.y); acc.y = fmaf(a.y, b.x, acc.y);
 }
+#endif
+GA_HD cf cconj(cf a) { return mk(a.x, -a.y); }
 
 // read-only global load
 GA_HD cf ldg(const cf *p)

@@ -281,19 +281,29 @@ template <int NF, bool LOAD> __device__ __forceinline__ void tm_move(uint32_t a,
     else if constexpr (NF >= 2) { if (LOAD) TmVec<2>::ld(a, v); else TmVec<2>::st(a, v); tm_move<NF - 2, LOAD>(a + 2, v + 2); }
 }
 constexpr uint32_t pow2_at_least(uint32_t x, uint32_t p = 32) { return p >= x ? p : pow2_at_least(x, p * 2); }
+#ifndef TM_MINB
+#define TM_MINB 2     // CTAs per SM the TMEM kernel is sized for
+#endif
 
 template <class G, int T, int NW, int GID>
-__global__ void __launch_bounds__(T, 2) cell_kernel_tm(const cf *__restrict__ xd, const cf *__restrict__ cext,
+__global__ void __launch_bounds__(T, TM_MINB) cell_kernel_tm(const cf *__restrict__ xd, const cf *__restrict__ cext,
                                                        const int *__restrict__ sv_of_block, const cf *__restrict__ tw,
                                                        int n_cells, int n_dop, int dmax, int wlen, CellStat *__restrict__ cells)
 {
     static_assert(T % 32 == 0, "tcgen05.ld/st are warp-collective: whole warps only");
-    constexpr int ITA = cdiv(G::NA, T), ITB = cdiv(G::NB, T), ITC = cdiv(G::NC, T);
     constexpr int NWARP = T / 32;
+    // Work is handed out in warp-tasks of 32 butterflies (task k = butterflies 32k..32k+31), warp w runs
+    // tasks w, w+NWARP, ...  (Rotating the map between the two CTAs of an SM to even out the load of the
+    // four sub-partitions was measured: no gain, and it made the summation order depend on the CTA.)
+    constexpr int NTA = cdiv(G::NA, 32), NTB = cdiv(G::NB, 32), NTC = cdiv(G::NC, 32);
+    constexpr int ITA = cdiv(NTA, NWARP), ITB = cdiv(NTB, NWARP), ITC = cdiv(NTC, NWARP);
     constexpr uint32_t COLS_THREAD = ITC * 2 * NW;                 // accumulator floats per thread
     constexpr uint32_t COL_SLOT = (COLS_THREAD + 7u) & ~7u;        // column range of one warp "row" (4 warps share the lanes)
     constexpr uint32_t TM_COLS = pow2_at_least(COL_SLOT * cdiv(NWARP, 4));
-    static_assert(TM_COLS <= 256, "two CTAs per SM must fit in the 512 TMEM columns");
+#ifndef GA_NO_TM_ASSERT
+    static_assert(TM_COLS * TM_MINB <= 512 || G::SMEM_ELEMS * sizeof(cf) * TM_MINB > 227 * 1024,
+                  "TM_MINB CTAs per SM must fit in the 512 TMEM columns");
+#endif
     extern __shared__ __align__(16) unsigned char smem_raw[];
     cf *sm = reinterpret_cast<cf *>(smem_raw);
     __shared__ float red_best[NWARP], red_sum[NWARP];
@@ -311,6 +321,7 @@ __global__ void __launch_bounds__(T, 2) cell_kernel_tm(const cf *__restrict__ xd
     const uint32_t tm_base = tm_base_s;
     // this warp's private window: lanes 32*(wid%4).., columns (wid/4)*COL_SLOT..
     const uint32_t tm_mine = tm_base + ((32u * (uint32_t)(wid & 3)) << 16) + (uint32_t)(wid >> 2) * COL_SLOT;
+    const int vw = wid;
 
     for (int cell = blockIdx.x; cell < n_cells; cell += gridDim.x) {
         const int blk = cell / n_dop, dop = cell - blk * n_dop - dmax;
@@ -327,52 +338,55 @@ __global__ void __launch_bounds__(T, 2) cell_kernel_tm(const cf *__restrict__ xd
             const cf *cs = cb + (size_t)sp * (2 * G::N2) + eoff;
 #pragma unroll
             for (int it = 0; it < ITA; it++) {
-                const int j = tid + it * T;
-                if (ITA * T == G::NA || j < G::NA) cell_passA<G>(j, s, xs, cs, tw, sm);
+                const int j = (vw + it * NWARP) * 32 + lane;
+                if (j < G::NA) cell_passA<G>(j, s, xs, cs, tw, sm);
             }
             __syncthreads();
 #pragma unroll
             for (int it = 0; it < ITB; it++) {
-                const int j = tid + it * T;
-                if (ITB * T == G::NB || j < G::NB) passB<G, +1>(j, s, tw, sm);
+                const int j = (vw + it * NWARP) * 32 + lane;
+                if (j < G::NB) passB<G, +1>(j, s, tw, sm);
             }
             __syncthreads();
             const cf *ks = c_ktab[GID] + s * G::RC;
 #pragma unroll
             for (int it = 0; it < ITC; it++) {
-                // every lane runs the butterfly (out-of-range lanes redo the last one) so that the
-                // warp-collective TMEM accesses below are never under divergence
-                const int j = tid + it * T;
-                const bool act = (ITC * T == G::NC) || j < G::NC;
-                const int jc = act ? j : G::NC - 1;
-                cf p[G::RC];
-                const int tau0 = passC<G, +1>(jc, sm, p);
-                float a[2 * NW];
-                const uint32_t col = tm_mine + (uint32_t)(it * 2 * NW);
-                if (s == 0) {
+                const int task = vw + it * NWARP;
+                if (task < NTC) {          // warp-uniform
+                    // every lane runs the butterfly (lanes past the end redo the last one) so that the
+                    // warp-collective TMEM accesses below are never under divergence
+                    const int j = task * 32 + lane;
+                    const bool act = j < G::NC;
+                    const int jc = act ? j : G::NC - 1;
+                    cf p[G::RC];
+                    const int tau0 = passC<G, +1>(jc, sm, p);
+                    float a[2 * NW];
+                    const uint32_t col = tm_mine + (uint32_t)(it * 2 * NW);
+                    if (s == 0) {
 #pragma unroll
-                    for (int w = 0; w < NW; w++) { a[2 * w] = p[w].x; a[2 * w + 1] = p[w].y; }   // ktab[0][w] = 1
-                } else {
-                    tm_move<2 * NW, true>(col, a);
-                    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                        for (int w = 0; w < NW; w++) { a[2 * w] = p[w].x; a[2 * w + 1] = p[w].y; }   // ktab[0][w] = 1
+                    } else {
+                        tm_move<2 * NW, true>(col, a);
+                        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
-                    for (int w = 0; w < NW; w++) {
-                        cf t = mk(a[2 * w], a[2 * w + 1]);
-                        cfma(t, p[w], ks[w]);
-                        a[2 * w] = t.x; a[2 * w + 1] = t.y;
+                        for (int w = 0; w < NW; w++) {
+                            cf t = mk(a[2 * w], a[2 * w + 1]);
+                            cfma(t, p[w], ks[w]);
+                            a[2 * w] = t.x; a[2 * w + 1] = t.y;
+                        }
                     }
-                }
-                if (s < G::N1 - 1) {
-                    tm_move<2 * NW, false>(col, a);
-                } else if (act) {
-                    // last sub-sequence: the outputs are complete -> power, first max, sum (:190-194)
+                    if (s < G::N1 - 1) {
+                        tm_move<2 * NW, false>(col, a);
+                    } else if (act) {
+                        // last sub-sequence: the outputs are complete -> power, first max, sum (:190-194)
 #pragma unroll
-                    for (int w = 0; w < NW; w++) {
-                        const int tau = tau0 + G::OUT_STRIDE * w;
-                        if (tau < wlen) {
-                            const float pwr = fmaf(a[2 * w], a[2 * w], a[2 * w + 1] * a[2 * w + 1]);
-                            if (pwr > best || (pwr == best && tau < besti)) { best = pwr; besti = tau; }
-                            sum += pwr;
+                        for (int w = 0; w < NW; w++) {
+                            const int tau = tau0 + G::OUT_STRIDE * w;
+                            if (tau < wlen) {
+                                const float pwr = fmaf(a[2 * w], a[2 * w], a[2 * w + 1] * a[2 * w + 1]);
+                                if (pwr > best || (pwr == best && tau < besti)) { best = pwr; besti = tau; }
+                                sum += pwr;
+                            }
                         }
                     }
                 }

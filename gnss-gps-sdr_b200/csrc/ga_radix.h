@@ -53,10 +53,10 @@ template <int DIR> struct Radix<2, DIR> {
 template <int DIR> struct Radix<4, DIR> {
     static GA_HD void run(cf (&x)[4])
     {
-        cf s0 = cadd(x[0], x[2]), d0 = csub(x[0], x[2]);
-        cf s1 = cadd(x[1], x[3]), d1 = cmul_i<DIR>(csub(x[1], x[3]));
-        x[0] = cadd(s0, s1); x[1] = cadd(d0, d1);
-        x[2] = csub(s0, s1); x[3] = csub(d0, d1);
+        const cf s0 = cadd(x[0], x[2]), d0 = csub(x[0], x[2]);
+        const cf s1 = cadd(x[1], x[3]), d1 = csub(x[1], x[3]);
+        x[0] = cadd(s0, s1); x[1] = cadd_i<DIR>(d0, d1);     // d0 + DIR*i*d1
+        x[2] = csub(s0, s1); x[3] = csub_i<DIR>(d0, d1);
     }
 };
 
@@ -64,18 +64,16 @@ template <int DIR> struct Radix<5, DIR> {
     static GA_HD void run(cf (&x)[5])
     {
         constexpr float c1 = (float)cx_cos2pi(1, 5), c2 = (float)cx_cos2pi(2, 5);
-        constexpr float s1 = (float)(DIR * cx_sin2pi(1, 5)), s2 = (float)(DIR * cx_sin2pi(2, 5));
-        cf t1 = cadd(x[1], x[4]), t3 = csub(x[1], x[4]);
-        cf t2 = cadd(x[2], x[3]), t4 = csub(x[2], x[3]);
-        cf b1 = mk(fmaf(c2, t2.x, fmaf(c1, t1.x, x[0].x)), fmaf(c2, t2.y, fmaf(c1, t1.y, x[0].y)));
-        cf b2 = mk(fmaf(c1, t2.x, fmaf(c2, t1.x, x[0].x)), fmaf(c1, t2.y, fmaf(c2, t1.y, x[0].y)));
-        cf d1 = mk(fmaf(s2, t4.x, s1 * t3.x), fmaf(s2, t4.y, s1 * t3.y));
-        cf d2 = mk(fmaf(-s1, t4.x, s2 * t3.x), fmaf(-s1, t4.y, s2 * t3.y));
+        constexpr float s1 = (float)cx_sin2pi(1, 5), s2 = (float)cx_sin2pi(2, 5);
+        const cf t1 = cadd(x[1], x[4]), t3 = csub(x[1], x[4]);
+        const cf t2 = cadd(x[2], x[3]), t4 = csub(x[2], x[3]);
+        const cf b1 = caxpy(caxpy(x[0], t1, c1), t2, c2);
+        const cf b2 = caxpy(caxpy(x[0], t1, c2), t2, c1);
+        const cf d1 = caxpy(cscale(t3, s1), t4, s2);         // X1 = b1 + DIR*i*d1
+        const cf d2 = caxpy(cscale(t3, s2), t4, -s1);
         x[0] = cadd(x[0], cadd(t1, t2));
-        x[1] = mk(b1.x - d1.y, b1.y + d1.x);   // b1 + i*d1
-        x[4] = mk(b1.x + d1.y, b1.y - d1.x);
-        x[2] = mk(b2.x - d2.y, b2.y + d2.x);
-        x[3] = mk(b2.x + d2.y, b2.y - d2.x);
+        x[1] = cadd_i<DIR>(b1, d1); x[4] = csub_i<DIR>(b1, d1);
+        x[2] = cadd_i<DIR>(b2, d2); x[3] = csub_i<DIR>(b2, d2);
     }
 };
 

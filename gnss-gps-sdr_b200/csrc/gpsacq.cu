@@ -14,6 +14,11 @@
 #include <algorithm>
 
 #include "../../include/gpsacq.h"
+
+#ifndef CELL_MINB
+#define CELL_MINB 2        // CTAs per SM the cell kernels are sized for (registers, smem carveout, TMEM columns)
+#endif
+#define TM_MINB CELL_MINB
 #include "ga_kernels.cuh"
 #include "ga_tables.h"
 
@@ -31,9 +36,9 @@ typedef Geom<5, 20, 20, 20, GA_G8000_ROT != 0> G8000;  // W <= 8000 (FS <= 8 MHz
 typedef Geom<4, 25, 20, 20> G10000;    // W <= 10000  (FS <= 10 MHz, e.g. 8.184 MHz, 10 MHz)
 enum { GID_4000 = 0, GID_8000 = 1, GID_10000 = 2 };
 
-#define CELL_T_4000 224
+#define CELL_T_4000 256
 #ifndef CELL_T_8000
-#define CELL_T_8000 224     // 7 whole warps (tcgen05.ld/st are warp-collective); 400 butterflies per pass
+#define CELL_T_8000 448     // 14 whole warps, one 32-butterfly task each (13 tasks per pass), 72 registers, 2 CTAs/SM
 #endif
 #define CELL_T_10000 256
 #define FWD_T 256
@@ -87,9 +92,6 @@ struct gpsacq {
     } while (0)
 
 // ---- kernel dispatch ------------------------------------------------------------------
-#ifndef CELL_MINB
-#define CELL_MINB 2
-#endif
 #ifndef CELL_MAXREG
 #define CELL_MAXREG 144      // 2 CTAs x 7 warps x 32 lanes x 144 regs <= 64K registers per SM
 #endif
@@ -112,8 +114,13 @@ static int launch_cells_t(gpsacq *h, size_t n_blocks, const int *d_sv)
 {
     const int n_cells = (int)(n_blocks * (size_t)h->ndop);
     const int grid = std::min(n_cells, h->cell_ctas);
-    CellKernel<G, T, NW, GID>::get()<<<grid, T, h->cell_smem, h->stream>>>(
-        h->d_xd, h->d_cext, d_sv, h->d_tw, n_cells, h->ndop, h->dmax, h->w, h->d_cells);
+    if constexpr (GA_CELL_TMEM != 0 && !G::ROT && T % 32 == 0) {
+        cell_kernel_tm<G, T, NW, GID><<<grid, T, h->cell_smem, h->stream>>>(
+            h->d_xd, h->d_cext, d_sv, h->d_tw, n_cells, h->ndop, h->dmax, h->w, h->d_cells);
+    } else {
+        CellKernel<G, T, NW, GID>::get()<<<grid, T, h->cell_smem, h->stream>>>(
+            h->d_xd, h->d_cext, d_sv, h->d_tw, n_cells, h->ndop, h->dmax, h->w, h->d_cells);
+    }
     CUDA_TRY(h, cudaGetLastError());
     return 0;
 }
