@@ -598,24 +598,36 @@ cell_kernel_rot(const cf *__restrict__ xd, const cf *__restrict__ cext, const in
 __global__ void best_kernel(const CellStat *__restrict__ cells, const int *__restrict__ sv_of_block,
                             int n_blocks, int n_dop, int dmax, int wlen, Peak *__restrict__ peaks)
 {
-    const int blk = blockIdx.x * blockDim.x + threadIdx.x;
+    // one warp per chunk: lanes take Doppler bins k, k+32, ... in ascending order, then a shuffle
+    // reduction that prefers the higher snr and, on equal snr, the LOWER bin -- the same winner as the
+    // reference's ascending strictly-greater scan.
+    const int blk = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (blk >= n_blocks) return;
     const CellStat *c = cells + (size_t)blk * n_dop;
-    Peak p; p.snr = 0.0f; p.max_pwr = 0.0f; p.tot_pwr = 0.0f; p.lo_shift = 0; p.ca_shift = 0;
-    float max_snr = 0.0f;
-    for (int k = 0; k < n_dop; k++) {
-        const float ave = __fdiv_rn(c[k].tot_pwr, (float)wlen);
-        const float snr = __fdiv_rn(c[k].max_pwr, ave);
-        if (snr > max_snr) {
-            max_snr = snr; p.lo_shift = k - dmax; p.ca_shift = c[k].max_idx;
-            p.max_pwr = c[k].max_pwr; p.tot_pwr = c[k].tot_pwr;
-        }
+    float snr = 0.0f;        // max_snr starts at 0: bins with snr <= 0 (or NaN) never win (:173,:198)
+    int k = 0x7fffffff;
+    for (int i = lane; i < n_dop; i += 32) {
+        const float ave = __fdiv_rn(c[i].tot_pwr, (float)wlen);
+        const float v = __fdiv_rn(c[i].max_pwr, ave);
+        if (v > snr) { snr = v; k = i; }
     }
-    p.snr = max_snr;
-    p.sv = sv_of_block ? sv_of_block[blk] : (blk & 31);
-    p.flags = (max_snr < 25.0f) ? 0 : 1;
-    p.reserved = 0;
-    peaks[blk] = p;
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+        const float os = __shfl_down_sync(0xffffffffu, snr, off);
+        const int ok = __shfl_down_sync(0xffffffffu, k, off);
+        if (os > snr || (os == snr && ok < k)) { snr = os; k = ok; }
+    }
+    if (lane == 0) {
+        Peak p;
+        p.snr = snr; p.max_pwr = 0.0f; p.tot_pwr = 0.0f; p.lo_shift = 0; p.ca_shift = 0;
+        if (k != 0x7fffffff) {
+            p.lo_shift = k - dmax; p.ca_shift = c[k].max_idx; p.max_pwr = c[k].max_pwr; p.tot_pwr = c[k].tot_pwr;
+        }
+        p.sv = sv_of_block ? sv_of_block[blk] : (blk & 31);
+        p.flags = (snr < 25.0f) ? 0 : 1;
+        p.reserved = 0;
+        peaks[blk] = p;
+    }
 }
 
 // natural-order readback helpers for the parity probes -------------------------------

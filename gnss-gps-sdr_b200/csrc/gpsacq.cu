@@ -419,7 +419,7 @@ int gpsacq_search_blocks_device(gpsacq_t *h, const uint8_t *d_bits, size_t n_blo
     rc = launch_cells(h, n_blocks, d_sv);
     if (rc) return rc;
     CUDA_TRY(h, cudaEventRecord(h->ev[2], h->stream));
-    best_kernel<<<(unsigned)((n_blocks + 127) / 128), 128, 0, h->stream>>>(h->d_cells, d_sv, (int)n_blocks, h->ndop, h->dmax, h->w, (Peak *)d_out);
+    best_kernel<<<(unsigned)((n_blocks + 3) / 4), 128, 0, h->stream>>>(h->d_cells, d_sv, (int)n_blocks, h->ndop, h->dmax, h->w, (Peak *)d_out);
     CUDA_TRY(h, cudaGetLastError());
     CUDA_TRY(h, cudaEventRecord(h->ev[3], h->stream));
     h->have_batch = true;
