@@ -26,6 +26,7 @@ class GpsAcqError(RuntimeError):
 class _Cfg(C.Structure):
     _fields_ = [("fc", C.c_double), ("fs", C.c_double), ("max_fo", C.c_double),
                 ("fft_len", C.c_int32), ("device", C.c_int32), ("max_blocks", C.c_int32),
+                ("mode", C.c_int32), ("doppler_step", C.c_double), ("noncoh_blocks", C.c_int32),
                 ("reserved", C.c_int32)]
 
 
@@ -33,7 +34,8 @@ class _Info(C.Structure):
     _fields_ = [(n, C.c_int32) for n in
                 ("abi_version", "fft_len", "n1", "n2", "window", "dmax", "n_doppler", "chunk_bytes",
                  "max_blocks", "device", "sm_count", "cell_ctas", "cell_threads", "cell_smem_bytes")] + \
-               [("bytes_per_corr", C.c_int64)]
+               [("bytes_per_corr", C.c_int64), ("mode", C.c_int32), ("noncoh_blocks", C.c_int32),
+                ("block_bytes", C.c_int32), ("max_acq", C.c_int32), ("doppler_step", C.c_double)]
 
 
 PEAK_DTYPE = np.dtype([("snr", "<f4"), ("max_pwr", "<f4"), ("tot_pwr", "<f4"), ("lo_shift", "<i4"),
@@ -67,6 +69,8 @@ def load_library() -> C.CDLL:
         "gpsacq_synchronize": (C.c_int, [vp]),
         "gpsacq_search_blocks": (C.c_int, [vp, vp, C.c_size_t, vp, vp]),
         "gpsacq_search_blocks_device": (C.c_int, [vp, vp, C.c_size_t, vp, vp]),
+        "gpsacq_acquire": (C.c_int, [vp, vp, C.c_size_t, vp]),
+        "gpsacq_acquire_device": (C.c_int, [vp, vp, C.c_size_t, vp]),
         "gpsacq_stage_times": (C.c_int, [vp, f32p]),
         "gpsacq_get_replica_time": (C.c_int, [vp, C.c_int, vp]),
         "gpsacq_get_replica_spectrum": (C.c_int, [vp, C.c_int, vp]),
@@ -82,7 +86,7 @@ def load_library() -> C.CDLL:
 
 ABI_SYMBOLS = ("gpsacq_create", "gpsacq_destroy", "gpsacq_last_error", "gpsacq_get_info",
                "gpsacq_set_stream", "gpsacq_synchronize", "gpsacq_search_blocks",
-               "gpsacq_search_blocks_device", "gpsacq_stage_times", "gpsacq_get_replica_time",
+               "gpsacq_search_blocks_device", "gpsacq_acquire", "gpsacq_acquire_device", "gpsacq_stage_times", "gpsacq_get_replica_time",
                "gpsacq_get_replica_spectrum", "gpsacq_get_block_spectrum", "gpsacq_get_cell_stats")
 
 
@@ -92,10 +96,12 @@ class Acquisition:
     fc, fs, max_fo are the reference's FC / FS / max_fo globals (c/gps_offline.h:23-25).
     """
 
-    def __init__(self, fc: float, fs: float, max_fo: float = 5000.0, device: int = -1, max_blocks: int = 0):
+    def __init__(self, fc: float, fs: float, max_fo: float = 5000.0, device: int = -1, max_blocks: int = 0,
+                 mode: int = 0, doppler_step: float = 0.0, noncoh_blocks: int = 1):
         self._lib = load_library()
         self._h = C.c_void_p()
-        cfg = _Cfg(fc=fc, fs=fs, max_fo=max_fo, fft_len=0, device=device, max_blocks=max_blocks, reserved=0)
+        cfg = _Cfg(fc=fc, fs=fs, max_fo=max_fo, fft_len=0, device=device, max_blocks=max_blocks, mode=mode,
+                   doppler_step=doppler_step, noncoh_blocks=noncoh_blocks, reserved=0)
         rc = self._lib.gpsacq_create(C.byref(cfg), C.byref(self._h))
         if rc != 0:
             msg = self._lib.gpsacq_last_error(None)
@@ -157,6 +163,23 @@ class Acquisition:
             svp = sv.ctypes.data
         self._check(self._lib.gpsacq_search_blocks(self._h, buf.ctypes.data, n_blocks, svp, out.ctypes.data))
         return out
+
+    # -- GRID mode (mode=1): 1 ms blocks, explicit Doppler grid, K-block non-coherent sum --------------
+    @property
+    def acq_bytes(self) -> int:
+        return self.info["block_bytes"] * self.info["noncoh_blocks"]
+
+    def acquire(self, bits) -> np.ndarray:
+        """GRID mode: every `acq_bytes` of `bits` is one acquisition of all 32 PRNs; returns 32 records each."""
+        buf = np.ascontiguousarray(np.frombuffer(bits, dtype=np.uint8) if not isinstance(bits, np.ndarray) else bits,
+                                   dtype=np.uint8)
+        n_acq = buf.size // self.acq_bytes
+        out = np.zeros(n_acq * NUM_SATS, dtype=PEAK_DTYPE)
+        self._check(self._lib.gpsacq_acquire(self._h, buf.ctypes.data, n_acq, out.ctypes.data))
+        return out
+
+    def acquire_device(self, d_bits_ptr: int, n_acq: int, d_out_ptr: int):
+        self._check(self._lib.gpsacq_acquire_device(self._h, d_bits_ptr, n_acq, d_out_ptr))
 
     def search_blocks_device(self, d_bits_ptr: int, n_blocks: int, d_sv_ptr: int | None, d_out_ptr: int):
         """Asynchronous device-pointer variant (raw CUDA device addresses)."""

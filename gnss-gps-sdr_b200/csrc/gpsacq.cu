@@ -20,6 +20,7 @@
 #endif
 #define TM_MINB CELL_MINB
 #include "ga_kernels.cuh"
+#include "ga_grid.cuh"
 #include "ga_tables.h"
 
 using namespace ga;
@@ -35,6 +36,11 @@ typedef Geom<10, 20, 20, 10> G4000;    // W <= 4000   (FS <= 4 MHz, e.g. rtl-sdr
 typedef Geom<5, 20, 20, 20, GA_G8000_ROT != 0> G8000;  // W <= 8000 (FS <= 8 MHz, e.g. 5.456 MHz); rotating smem layouts
 typedef Geom<4, 25, 20, 20> G10000;    // W <= 10000  (FS <= 10 MHz, e.g. 8.184 MHz, 10 MHz)
 enum { GID_4000 = 0, GID_8000 = 1, GID_10000 = 2 };
+// GRID mode: L = 2*N2 >= 2W (linear-correlation embedding of the W-point circular correlation)
+typedef Geom<2, 20, 20, 10> H4000;     // L = 8000,  W <= 4000
+typedef Geom<2, 20, 20, 20> H8000;     // L = 16000, W <= 8000
+typedef Geom<2, 25, 20, 20> H10000;    // L = 20000, W <= 10000
+enum { HID_4000 = 3, HID_8000 = 4, HID_10000 = 5 };
 
 #define CELL_T_4000 256
 #ifndef CELL_T_8000
@@ -59,6 +65,10 @@ struct gpsacq {
     gpsacq_cfg cfg;
     int gid, n, n1, n2, w, dmax, ndop, chunk_bytes, chunk_samples, cap, device, sm_count;
     int cell_ctas, cell_threads, cell_smem, cell_nw;
+    int mode, kblocks, wipe_m, block_bytes, cap_acq;
+    double step;
+    cf *d_wipe, *d_xg;
+    float *d_code_w;
     cudaStream_t own_stream, stream;
     cudaEvent_t ev[4];
     bool have_batch;
@@ -257,7 +267,7 @@ static void free_all(gpsacq *h)
     if (!h) return;
     cudaFree(h->d_tw); cudaFree(h->d_lo); cudaFree(h->d_chip_idx); cudaFree(h->d_blend_a); cudaFree(h->d_blend_b);
     cudaFree(h->d_repl_time); cudaFree(h->d_cext); cudaFree(h->d_xd); cudaFree(h->d_nat); cudaFree(h->d_bits);
-    cudaFree(h->d_sv); cudaFree(h->d_cells); cudaFree(h->d_peaks);
+    cudaFree(h->d_sv); cudaFree(h->d_wipe); cudaFree(h->d_xg); cudaFree(h->d_code_w); cudaFree(h->d_cells); cudaFree(h->d_peaks);
     cudaFreeHost(h->h_bits); cudaFreeHost(h->h_sv); cudaFreeHost(h->h_peaks);
     for (int i = 0; i < 4; i++) if (h->ev[i]) cudaEventDestroy(h->ev[i]);
     if (h->own_stream) cudaStreamDestroy(h->own_stream);
@@ -345,6 +355,165 @@ static int create_impl(gpsacq *h)
     return 0;
 }
 
+
+// =========================================================================================
+// GRID mode (include/gpsacq.h GPSACQ_MODE_GRID; semantics in SURVEY.md App. E)
+// =========================================================================================
+template <class H, int T, int NW, int HID> struct GridOps {
+    static int setup(gpsacq *h)
+    {
+        auto kern = grid_cell_kernel<H, T, NW, HID>;
+        h->cell_smem = (int)(H::SMEM_ELEMS * sizeof(cf));
+        h->cell_threads = T; h->cell_nw = NW;
+        CUDA_TRY(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, h->cell_smem));
+        const int want = CELL_MINB * (h->cell_smem + 2048);
+        int pct = (int)((want * 100LL + 228 * 1024 - 1) / (228 * 1024));
+        if (pct > 100) pct = 100;
+        CUDA_TRY(h, cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, pct));
+        h->cell_ctas = CELL_MINB * h->sm_count;      // TMEM kernels: see setup_cells_t
+        auto fk = fwd_grid_kernel<H, FWD_T, HID>;
+        CUDA_TRY(h, cudaFuncSetAttribute(fk, cudaFuncAttributeMaxDynamicSharedMemorySize, h->cell_smem));
+        return 0;
+    }
+    static int fwd_blocks(gpsacq *h, size_t n_blocks, const unsigned char *d_bits)
+    {
+        fwd_grid_kernel<H, FWD_T, HID><<<(unsigned)(n_blocks * h->ndop * H::N1), FWD_T, h->cell_smem, h->stream>>>(
+            d_bits, h->block_bytes, h->d_lo, h->d_wipe, h->w, h->ndop, h->dmax, h->wipe_m, h->d_tw, h->d_xg);
+        CUDA_TRY(h, cudaGetLastError());
+        return 0;
+    }
+    static int cells(gpsacq *h, size_t n_acq)
+    {
+        const int n_cells = (int)(n_acq * 32 * (size_t)h->ndop);
+        const int grid = std::min(n_cells, h->cell_ctas);
+        grid_cell_kernel<H, T, NW, HID><<<grid, T, h->cell_smem, h->stream>>>(h->d_xg, h->d_cext, h->d_tw, n_cells, h->ndop,
+                                                                            h->kblocks, h->w, h->d_cells);
+        CUDA_TRY(h, cudaGetLastError());
+        return 0;
+    }
+    static int replicas(gpsacq *h) { return launch_fwd_t<H, 1, HID>(h, 32, nullptr, h->d_cext); }
+    static int consts(gpsacq *h) { return upload_const_t<H, HID>(h); }
+};
+
+#define GRID_DISPATCH(h, CALL)                                                                              \
+    (h->gid == HID_4000    ? (h->cell_nw == 7 ? GridOps<H4000, 256, 7, HID_4000>::CALL : GridOps<H4000, 256, 10, HID_4000>::CALL)      \
+     : h->gid == HID_8000  ? (h->cell_nw == 14 ? GridOps<H8000, 448, 14, HID_8000>::CALL : GridOps<H8000, 448, 20, HID_8000>::CALL)    \
+                           : (h->cell_nw == 17 ? GridOps<H10000, 256, 17, HID_10000>::CALL : GridOps<H10000, 256, 20, HID_10000>::CALL))
+
+static int create_grid(gpsacq *h)
+{
+    const gpsacq_cfg &c = h->cfg;
+    if (!(c.fs > 0) || !(c.fc >= 0) || !(c.max_fo >= 0) || !(c.doppler_step > 0)) { h->err = "GRID mode needs fs, doppler_step > 0"; return GPSACQ_EINVAL; }
+    const double wd = c.fs / 1000.0, md = c.fs / c.doppler_step;
+    h->w = (int)llround(wd);
+    h->wipe_m = (int)llround(md);
+    if (fabs(wd - h->w) > 1e-9 || h->w % 8) { h->err = "GRID mode needs FS/1000 to be an integer multiple of 8 samples"; return GPSACQ_EINVAL; }
+    if (fabs(md - h->wipe_m) > 1e-6 * md) { h->err = "GRID mode needs FS/doppler_step to be an integer"; return GPSACQ_EINVAL; }
+    h->kblocks = c.noncoh_blocks > 0 ? c.noncoh_blocks : 1;
+    h->step = c.doppler_step;
+    h->dmax = (int)floor(c.max_fo / c.doppler_step + 1e-9);
+    h->ndop = 2 * h->dmax + 1;
+    h->block_bytes = h->w / 8;
+    h->chunk_bytes = h->block_bytes * h->kblocks;
+    h->chunk_samples = h->w;
+    if (h->w <= H4000::N2) { h->gid = HID_4000; h->n1 = 2; h->n2 = H4000::N2; h->cell_nw = h->w <= 7 * H4000::OUT_STRIDE ? 7 : 10; }
+    else if (h->w <= H8000::N2) { h->gid = HID_8000; h->n1 = 2; h->n2 = H8000::N2; h->cell_nw = h->w <= 14 * H8000::OUT_STRIDE ? 14 : 20; }
+    else if (h->w <= H10000::N2) { h->gid = HID_10000; h->n1 = 2; h->n2 = H10000::N2; h->cell_nw = h->w <= 17 * H10000::OUT_STRIDE ? 17 : 20; }
+    else { h->err = "sampling rates above 10 MHz are not supported yet"; return GPSACQ_EINVAL; }
+    h->n = h->n1 * h->n2;                                      // L
+
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0) {
+        h->err = std::string("no CUDA device available (") + cudaGetErrorString(e) + "); libgpsacq has no CPU fallback";
+        return GPSACQ_ECUDA;
+    }
+    if (c.device >= 0) { CUDA_TRY(h, cudaSetDevice(c.device)); }
+    CUDA_TRY(h, cudaGetDevice(&h->device));
+    cudaDeviceProp prop;
+    CUDA_TRY(h, cudaGetDeviceProperties(&prop, h->device));
+    if (prop.major < 10) { h->err = "libgpsacq is built for sm_100a (B200) only"; return GPSACQ_ECUDA; }
+    h->sm_count = prop.multiProcessorCount;
+    CUDA_TRY(h, cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking));
+    h->stream = h->own_stream;
+    for (int i = 0; i < 4; i++) CUDA_TRY(h, cudaEventCreate(&h->ev[i]));
+
+    // batch capacity: keep the block spectra of one batch under ~3 GB
+    const size_t per_acq = (size_t)h->kblocks * h->ndop * h->n * sizeof(cf);
+    size_t cap = (size_t)3 << 30;
+    cap = std::max<size_t>(1, cap / per_acq);
+    if (c.max_blocks > 0) cap = std::min<size_t>(cap, (size_t)c.max_blocks);
+    cap = std::min<size_t>(cap, 4096);
+    h->cap_acq = (int)cap;
+    h->cap = h->cap_acq;
+
+    const size_t L = (size_t)h->n, W = (size_t)h->w;
+    CUDA_TRY(h, cudaMalloc(&h->d_tw, L * sizeof(cf)));
+    CUDA_TRY(h, cudaMalloc(&h->d_wipe, (size_t)h->wipe_m * sizeof(cf)));
+    CUDA_TRY(h, cudaMalloc(&h->d_lo, W));
+    CUDA_TRY(h, cudaMalloc(&h->d_chip_idx, W * sizeof(unsigned short)));
+    CUDA_TRY(h, cudaMalloc(&h->d_blend_a, W * sizeof(float)));
+    CUDA_TRY(h, cudaMalloc(&h->d_blend_b, W * sizeof(float)));
+    CUDA_TRY(h, cudaMalloc(&h->d_code_w, 32 * W * sizeof(float)));
+    CUDA_TRY(h, cudaMalloc(&h->d_repl_time, 32 * L * sizeof(float)));
+    CUDA_TRY(h, cudaMalloc(&h->d_cext, 32 * 2 * L * sizeof(cf)));
+    CUDA_TRY(h, cudaMalloc(&h->d_xg, cap * per_acq));
+    CUDA_TRY(h, cudaMalloc(&h->d_nat, L * sizeof(cf)));
+    CUDA_TRY(h, cudaMalloc(&h->d_bits, cap * (size_t)h->chunk_bytes));
+    CUDA_TRY(h, cudaMalloc(&h->d_cells, cap * 32 * (size_t)h->ndop * sizeof(CellStat)));
+    CUDA_TRY(h, cudaMalloc(&h->d_peaks, cap * 32 * sizeof(Peak)));
+    CUDA_TRY(h, cudaMallocHost(&h->h_bits, cap * (size_t)h->chunk_bytes));
+    CUDA_TRY(h, cudaMallocHost(&h->h_peaks, cap * 32 * sizeof(Peak)));
+
+    std::vector<cf> tw = make_tw(h->n);
+    CUDA_TRY(h, cudaMemcpy(h->d_tw, tw.data(), L * sizeof(cf), cudaMemcpyHostToDevice));
+    std::vector<cf> wipe = make_tw(h->wipe_m);                 // exp(+2 pi i k/M); the wipe-off uses the conjugate
+    for (auto &v : wipe) v.y = -v.y;
+    CUDA_TRY(h, cudaMemcpy(h->d_wipe, wipe.data(), wipe.size() * sizeof(cf), cudaMemcpyHostToDevice));
+    int rc = GRID_DISPATCH(h, consts(h));
+    if (rc) return rc;
+    std::vector<unsigned char> lo;
+    build_lo_table(c.fc, c.fs, h->w, lo);                      // phase restarts at every block (App. E)
+    CUDA_TRY(h, cudaMemcpy(h->d_lo, lo.data(), lo.size(), cudaMemcpyHostToDevice));
+    std::vector<unsigned short> ci; std::vector<float> ba, bb;
+    build_code_nco(c.fs, h->w, ci, ba, bb);                    // one code period, same NCO + blend as SearchInit()
+    CUDA_TRY(h, cudaMemcpy(h->d_chip_idx, ci.data(), W * sizeof(unsigned short), cudaMemcpyHostToDevice));
+    CUDA_TRY(h, cudaMemcpy(h->d_blend_a, ba.data(), W * sizeof(float), cudaMemcpyHostToDevice));
+    CUDA_TRY(h, cudaMemcpy(h->d_blend_b, bb.data(), W * sizeof(float), cudaMemcpyHostToDevice));
+    rc = GRID_DISPATCH(h, setup(h));
+    if (rc) return rc;
+
+    SatTaps taps;
+    for (int sv = 0; sv < 32; sv++) { taps.t0[sv] = kTaps[sv][0]; taps.t1[sv] = kTaps[sv][1]; }
+    replica_time_kernel<<<32, 256, 0, h->stream>>>(taps, h->d_chip_idx, h->d_blend_a, h->d_blend_b, h->w, h->d_code_w);
+    CUDA_TRY(h, cudaGetLastError());
+    grid_replica_extend_kernel<<<dim3(16, 32), 256, 0, h->stream>>>(h->d_code_w, h->w, h->n, (float)((double)h->w / (double)h->n), h->d_repl_time);
+    CUDA_TRY(h, cudaGetLastError());
+    rc = GRID_DISPATCH(h, replicas(h));
+    if (rc) return rc;
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+static int acquire_device_impl(gpsacq *h, const uint8_t *d_bits, size_t n_acq, gpsacq_peak *d_out)
+{
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    CUDA_TRY(h, cudaEventRecord(h->ev[0], h->stream));
+    int rc = GRID_DISPATCH(h, fwd_blocks(h, n_acq * (size_t)h->kblocks, d_bits));
+    if (rc) return rc;
+    CUDA_TRY(h, cudaEventRecord(h->ev[1], h->stream));
+    rc = GRID_DISPATCH(h, cells(h, n_acq));
+    if (rc) return rc;
+    CUDA_TRY(h, cudaEventRecord(h->ev[2], h->stream));
+    const size_t nrec = n_acq * 32;
+    best_kernel<<<(unsigned)((nrec + 3) / 4), 128, 0, h->stream>>>(h->d_cells, nullptr, (int)nrec, h->ndop, h->dmax, h->w, (Peak *)d_out);
+    CUDA_TRY(h, cudaGetLastError());
+    CUDA_TRY(h, cudaEventRecord(h->ev[3], h->stream));
+    h->have_batch = true;
+    h->last_blocks = nrec;
+    return GPSACQ_OK;
+}
+
 // ---- ABI -------------------------------------------------------------------------------
 extern "C" {
 
@@ -355,7 +524,9 @@ int gpsacq_create(const gpsacq_cfg *cfg, gpsacq_t **out)
     gpsacq *h = new (std::nothrow) gpsacq();
     if (!h) { g_create_error = "out of host memory"; return GPSACQ_ENOMEM; }
     h->cfg = *cfg;
-    int rc = create_impl(h);
+    h->mode = cfg->mode;
+    if (cfg->mode != GPSACQ_MODE_REF && cfg->mode != GPSACQ_MODE_GRID) { g_create_error = "unknown mode"; delete h; return GPSACQ_EINVAL; }
+    int rc = cfg->mode == GPSACQ_MODE_GRID ? create_grid(h) : create_impl(h);
     if (rc) {
         g_create_error = h->err;
         free_all(h);
@@ -387,7 +558,11 @@ int gpsacq_get_info(const gpsacq_t *h, gpsacq_info *info)
     info->chunk_bytes = h->chunk_bytes; info->max_blocks = h->cap;
     info->device = h->device; info->sm_count = h->sm_count;
     info->cell_ctas = h->cell_ctas; info->cell_threads = h->cell_threads; info->cell_smem_bytes = h->cell_smem;
-    info->bytes_per_corr = 2LL * h->n * 8 + 16;
+    info->bytes_per_corr = 2LL * (h->mode == GPSACQ_MODE_GRID ? h->w : h->n) * 8 + 16;
+    info->mode = h->mode; info->noncoh_blocks = h->mode == GPSACQ_MODE_GRID ? h->kblocks : 1;
+    info->block_bytes = h->mode == GPSACQ_MODE_GRID ? h->block_bytes : h->chunk_bytes;
+    info->max_acq = h->mode == GPSACQ_MODE_GRID ? h->cap_acq : 0;
+    info->doppler_step = h->mode == GPSACQ_MODE_GRID ? h->step : h->cfg.fs / h->n;
     return GPSACQ_OK;
 }
 
@@ -409,6 +584,7 @@ int gpsacq_synchronize(gpsacq_t *h)
 int gpsacq_search_blocks_device(gpsacq_t *h, const uint8_t *d_bits, size_t n_blocks, const int32_t *d_sv, gpsacq_peak *d_out)
 {
     if (!h || !d_bits || !d_out) return GPSACQ_EINVAL;
+    if (h->mode != GPSACQ_MODE_REF) { h->err = "gpsacq_search_blocks needs a GPSACQ_MODE_REF handle"; return GPSACQ_EINVAL; }
     if (n_blocks == 0) return GPSACQ_OK;
     if (n_blocks > (size_t)h->cap) { h->err = "n_blocks exceeds max_blocks"; return GPSACQ_EINVAL; }
     CUDA_TRY(h, cudaSetDevice(h->device));
@@ -430,6 +606,7 @@ int gpsacq_search_blocks_device(gpsacq_t *h, const uint8_t *d_bits, size_t n_blo
 int gpsacq_search_blocks(gpsacq_t *h, const uint8_t *bits, size_t n_blocks, const int32_t *sv_of_block, gpsacq_peak *out)
 {
     if (!h || (!bits && n_blocks) || (!out && n_blocks)) return GPSACQ_EINVAL;
+    if (h->mode != GPSACQ_MODE_REF) { h->err = "gpsacq_search_blocks needs a GPSACQ_MODE_REF handle"; return GPSACQ_EINVAL; }
     CUDA_TRY(h, cudaSetDevice(h->device));
     for (size_t done = 0; done < n_blocks;) {
         const size_t nb = std::min((size_t)h->cap, n_blocks - done);
@@ -451,6 +628,34 @@ int gpsacq_search_blocks(gpsacq_t *h, const uint8_t *bits, size_t n_blocks, cons
     return GPSACQ_OK;
 }
 
+int gpsacq_acquire_device(gpsacq_t *h, const uint8_t *d_bits, size_t n_acq, gpsacq_peak *d_out)
+{
+    if (!h || !d_bits || !d_out) return GPSACQ_EINVAL;
+    if (h->mode != GPSACQ_MODE_GRID) { h->err = "gpsacq_acquire needs a GPSACQ_MODE_GRID handle"; return GPSACQ_EINVAL; }
+    if (n_acq == 0) return GPSACQ_OK;
+    if (n_acq > (size_t)h->cap_acq) { h->err = "n_acq exceeds the batch capacity (gpsacq_info.max_acq)"; return GPSACQ_EINVAL; }
+    return acquire_device_impl(h, d_bits, n_acq, d_out);
+}
+
+int gpsacq_acquire(gpsacq_t *h, const uint8_t *bits, size_t n_acq, gpsacq_peak *out)
+{
+    if (!h || (!bits && n_acq) || (!out && n_acq)) return GPSACQ_EINVAL;
+    if (h->mode != GPSACQ_MODE_GRID) { h->err = "gpsacq_acquire needs a GPSACQ_MODE_GRID handle"; return GPSACQ_EINVAL; }
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    for (size_t done = 0; done < n_acq;) {
+        const size_t na = std::min((size_t)h->cap_acq, n_acq - done);
+        memcpy(h->h_bits, bits + done * (size_t)h->chunk_bytes, na * (size_t)h->chunk_bytes);
+        CUDA_TRY(h, cudaMemcpyAsync(h->d_bits, h->h_bits, na * (size_t)h->chunk_bytes, cudaMemcpyHostToDevice, h->stream));
+        int rc = acquire_device_impl(h, h->d_bits, na, (gpsacq_peak *)h->d_peaks);
+        if (rc) return rc;
+        CUDA_TRY(h, cudaMemcpyAsync(h->h_peaks, h->d_peaks, na * 32 * sizeof(Peak), cudaMemcpyDeviceToHost, h->stream));
+        CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+        memcpy(out + done * 32, h->h_peaks, na * 32 * sizeof(Peak));
+        done += na;
+    }
+    return GPSACQ_OK;
+}
+
 int gpsacq_stage_times(gpsacq_t *h, float ms[4])
 {
     if (!h || !ms) return GPSACQ_EINVAL;
@@ -466,6 +671,7 @@ int gpsacq_stage_times(gpsacq_t *h, float ms[4])
 int gpsacq_get_replica_time(gpsacq_t *h, int sv, float *out)
 {
     if (!h || !out || sv < 0 || sv >= 32) return GPSACQ_EINVAL;
+    if (h->mode != GPSACQ_MODE_REF) { h->err = "probe needs a GPSACQ_MODE_REF handle"; return GPSACQ_EINVAL; }
     CUDA_TRY(h, cudaSetDevice(h->device));
     CUDA_TRY(h, cudaStreamSynchronize(h->stream));
     CUDA_TRY(h, cudaMemcpy(out, h->d_repl_time + (size_t)sv * h->n, (size_t)h->n * sizeof(float), cudaMemcpyDeviceToHost));
@@ -485,12 +691,14 @@ static int read_natural(gpsacq *h, const cf *src, int mode, float *out)
 int gpsacq_get_replica_spectrum(gpsacq_t *h, int sv, float *out)
 {
     if (!h || !out || sv < 0 || sv >= 32) return GPSACQ_EINVAL;
+    if (h->mode != GPSACQ_MODE_REF) { h->err = "probe needs a GPSACQ_MODE_REF handle"; return GPSACQ_EINVAL; }
     return read_natural(h, h->d_cext + (size_t)sv * 2 * h->n, 1, out);
 }
 
 int gpsacq_get_block_spectrum(gpsacq_t *h, size_t blk, float *out)
 {
     if (!h || !out) return GPSACQ_EINVAL;
+    if (h->mode != GPSACQ_MODE_REF) { h->err = "probe needs a GPSACQ_MODE_REF handle"; return GPSACQ_EINVAL; }
     if (!h->have_batch || blk >= h->last_blocks) { h->err = "block index outside the last batch"; return GPSACQ_ESTATE; }
     return read_natural(h, h->d_xd + blk * (size_t)h->n, 0, out);
 }

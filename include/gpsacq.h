@@ -51,7 +51,7 @@
 extern "C" {
 #endif
 
-#define GPSACQ_ABI_VERSION 1
+#define GPSACQ_ABI_VERSION 2
 
 #define GPSACQ_OK        0
 #define GPSACQ_EINVAL   (-1)   /* bad argument / unsupported configuration        */
@@ -70,9 +70,21 @@ typedef struct gpsacq_cfg {
     double  max_fo;      /* Doppler search half-span (extern double max_fo, :25)               */
     int32_t fft_len;     /* 0 = GPSACQ_FFT_LEN; only 40000 is supported                        */
     int32_t device;      /* CUDA device ordinal; -1 = current device                           */
-    int32_t max_blocks;  /* batch capacity in chunks; 0 = 512 (16 runs of 32 PRNs)             */
+    int32_t max_blocks;  /* REF: batch capacity in chunks, 0 = 512 (16 runs of 32 PRNs);
+                            GRID: batch capacity in acquisitions, 0 = automatic                    */
+    int32_t mode;        /* GPSACQ_MODE_REF (0, the reference's semantics) or GPSACQ_MODE_GRID      */
+    double  doppler_step;/* GRID only: Doppler bin spacing in Hz; FS/doppler_step must be an integer */
+    int32_t noncoh_blocks;/* GRID only: K = number of 1 ms blocks summed non-coherently (>= 1)       */
     int32_t reserved;
 } gpsacq_cfg;
+
+#define GPSACQ_MODE_REF  0   /* N = 40000 coherent window, bins of FS/N, one chunk per PRN
+                                (c/search_offline.cpp as it is)                                     */
+#define GPSACQ_MODE_GRID 1   /* generalised grid of BASELINE.json configs[1..4] (NOT in the reference;
+                                definition in SURVEY.md App. E / DESIGN.md section 10): 1 ms coherent
+                                blocks of W = FS/1000 samples shared by all 32 PRNs, Doppler bins
+                                d*doppler_step for |d*doppler_step| <= max_fo with time-domain
+                                wipe-off, W-point circular correlation, K-block non-coherent sum    */
 
 /* One record per searched chunk = what Correlate() returns plus its inputs to the
  * snr division (c/search_offline.cpp:196-200). */
@@ -109,7 +121,13 @@ typedef struct gpsacq_info {
     int32_t cell_ctas;     /* persistent CTAs of the cell kernel                   */
     int32_t cell_threads;
     int32_t cell_smem_bytes;
-    int64_t bytes_per_corr;/* algorithmic bytes per (PRN,Doppler) correlation: 2*N*8+16 */
+    int64_t bytes_per_corr;/* algorithmic bytes per (PRN,Doppler) correlation: 2*N*8+16
+                              (REF: N = fft_len; GRID: N = window, per coherent block)   */
+    int32_t mode;          /* GPSACQ_MODE_*                                        */
+    int32_t noncoh_blocks; /* K (1 in REF mode)                                    */
+    int32_t block_bytes;   /* GRID: bytes per 1 ms block = window/8                */
+    int32_t max_acq;       /* GRID: acquisitions per internal batch                */
+    double  doppler_step;  /* Hz between Doppler bins (REF: FS/fft_len)            */
 } gpsacq_info;
 
 /* Number of kernels this library launches for a batch (for bench.py's gpu_launches). */
@@ -136,6 +154,13 @@ int  gpsacq_search_blocks(gpsacq_t *h, const uint8_t *packed_bits, size_t n_bloc
  * d_sv_of_block may be NULL. */
 int  gpsacq_search_blocks_device(gpsacq_t *h, const uint8_t *d_packed_bits, size_t n_blocks,
                                  const int32_t *d_sv_of_block, gpsacq_peak *d_out);
+
+/* GRID mode: n_acq acquisitions, each over noncoh_blocks consecutive 1 ms blocks of packed_bits
+ * (n_acq * noncoh_blocks * block_bytes bytes, LSB first).  All 32 PRNs are searched on the same
+ * blocks; out receives 32 records per acquisition (PRN order), lo_shift = Doppler bin index d
+ * (Doppler = d * doppler_step Hz), ca_shift = code phase in samples.  Host buffers / device buffers. */
+int  gpsacq_acquire(gpsacq_t *h, const uint8_t *packed_bits, size_t n_acq, gpsacq_peak *out);
+int  gpsacq_acquire_device(gpsacq_t *h, const uint8_t *d_packed_bits, size_t n_acq, gpsacq_peak *d_out);
 
 /* Elapsed milliseconds of the stages of the most recent batch, measured with CUDA
  * events on the launching stream: [0] unpack+mix+forward FFT kernel, [1] cell kernel

@@ -53,6 +53,15 @@ def _lib() -> C.CDLL:
     lib.oracle_search_code.argtypes = [C.c_int, C.c_int]
     lib.oracle_replica_time.argtypes = [C.c_double, C.c_int, C.c_int, vp]
     lib.oracle_lo_table.argtypes = [C.c_double, C.c_double, C.c_int, vp]
+    lib.oracle_grid_create.restype = vp
+    lib.oracle_grid_create.argtypes = [C.c_double, C.c_double, C.c_double, C.c_double, C.c_int]
+    lib.oracle_grid_destroy.argtypes = [vp]
+    lib.oracle_grid_num_doppler.restype = C.c_int
+    lib.oracle_grid_num_doppler.argtypes = [vp]
+    lib.oracle_grid_window.restype = C.c_int
+    lib.oracle_grid_window.argtypes = [vp]
+    lib.oracle_grid_acquire.restype = C.c_int
+    lib.oracle_grid_acquire.argtypes = [vp, vp, vp, vp, vp, vp]
     return lib
 
 
@@ -143,6 +152,45 @@ class Oracle:
         if rc:
             raise MemoryError("oracle_search_blocks failed")
         return out
+
+
+class GridOracle:
+    """GRID-mode definition with true W-point FFTs; see gpsacq_oracle.c."""
+
+    def __init__(self, fc: float, fs: float, max_fo: float, step: float, kblocks: int = 1):
+        self._l = lib()
+        self._h = self._l.oracle_grid_create(fc, fs, max_fo, step, kblocks)
+        if not self._h:
+            raise MemoryError("oracle_grid_create failed")
+        self.n_doppler = self._l.oracle_grid_num_doppler(self._h)
+        self.dmax = (self.n_doppler - 1) // 2
+        self.window = self._l.oracle_grid_window(self._h)
+        self.kblocks = kblocks
+        self.acq_bytes = kblocks * self.window // 8
+
+    def __del__(self):
+        try:
+            if self._h:
+                self._l.oracle_grid_destroy(self._h)
+                self._h = None
+        except Exception:
+            pass
+
+    def acquire(self, bits, want_cells: bool = False):
+        buf = np.ascontiguousarray(np.frombuffer(bits, np.uint8) if not isinstance(bits, np.ndarray) else bits)
+        n_acq = buf.size // self.acq_bytes
+        out = np.zeros(n_acq * 32, PEAK_DTYPE)
+        cells = []
+        for a in range(n_acq):
+            cm = np.zeros((32, self.n_doppler), np.float32)
+            ci = np.zeros((32, self.n_doppler), np.int32)
+            ct = np.zeros((32, self.n_doppler), np.float32)
+            sub = np.ascontiguousarray(buf[a * self.acq_bytes:(a + 1) * self.acq_bytes])
+            one = np.zeros(32, PEAK_DTYPE)
+            self._l.oracle_grid_acquire(self._h, sub.ctypes.data, one.ctypes.data, cm.ctypes.data, ci.ctypes.data, ct.ctypes.data)
+            out[a * 32:(a + 1) * 32] = one
+            cells.append((cm, ci, ct))
+        return (out, cells) if want_cells else out
 
 
 def mkl_env() -> dict:

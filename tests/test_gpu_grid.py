@@ -1,0 +1,95 @@
+"""GPU tests of GRID mode (BASELINE.json configs[1..4]: 1 ms coherent blocks, explicit Doppler grid,
+K-block non-coherent sums).  The reference has no such mode, so parity is against the oracle's
+definition (oracle/gpsacq_oracle.c, true W-point FFTs) -- "parity unpinned by the reference"."""
+import importlib
+
+import numpy as np
+import pytest
+
+from conftest import CAPTURES, compare_peaks
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def siggen(ga):
+    return importlib.import_module("gnss_gps_sdr_b200.siggen")
+
+
+CASES = [
+    # fs, fc, max_fo, step, K, n_acq, cn0
+    (5.456e6, 4.092e6, 5000.0, 500.0, 1, 3, 50.0),      # configs[1]
+    (8.184e6, 2.046e6, 5000.0, 500.0, 1, 2, 50.0),      # configs[2]
+    (2.8e6, 0.62e6, 10000.0, 250.0, 4, 2, 47.0),        # configs[3] shape (K>1, 250 Hz), reduced span for the CPU oracle
+    (8.184e6, 2.046e6, 3000.0, 100.0, 3, 1, 47.0),      # configs[4] shape (100 Hz step, K>1), reduced span
+]
+
+
+@pytest.mark.parametrize("fs,fc,max_fo,step,K,n_acq,cn0", CASES)
+def test_grid_vs_oracle(ga, oracle_mod, siggen, fs, fc, max_fo, step, K, n_acq, cn0):
+    W = int(round(fs / 1000))
+    sats = siggen.default_constellation(fs, cn0_dbhz=cn0, seed=int(fs) % 1000, max_doppler=0.9 * max_fo)
+    bits = siggen.synth_capture(W * K * n_acq, fs, fc, sats, seed=11)
+    acq = ga.Acquisition(fc, fs, max_fo, mode=1, doppler_step=step, noncoh_blocks=K)
+    try:
+        info = acq.info
+        assert info["mode"] == 1 and info["window"] == W and info["noncoh_blocks"] == K
+        assert info["n_doppler"] == 2 * int(max_fo // step) + 1 and info["block_bytes"] == W // 8
+        got = acq.acquire(bits)
+        g = oracle_mod.GridOracle(fc, fs, max_fo, step, K)
+        ref, cells = g.acquire(bits, want_cells=True)
+        assert len(got) == len(ref) == 32 * n_acq
+        assert np.array_equal(got["sv"], np.arange(32 * n_acq) % 32)
+        compare_peaks(got, ref)
+        # per-cell statistics of the last acquisition, two PRNs
+        for prn in (sats[0]["prn"], 3):
+            cs = acq.cell_stats((n_acq - 1) * 32 + prn - 1)
+            cm, ci, ct = cells[-1]
+            assert np.abs(cs["max_pwr"] / cm[prn - 1] - 1).max() <= 3e-5
+            assert np.abs(cs["tot_pwr"] / ct[prn - 1] - 1).max() <= 3e-5
+            diff = cs["max_idx"] != ci[prn - 1]
+            assert diff.sum() <= 1
+        # every generated satellite strong enough to clear the threshold sits at its Doppler bin
+        for s in sats:
+            for a in range(n_acq):
+                p = got[a * 32 + s["prn"] - 1]
+                if p["snr"] >= 30:
+                    assert abs(p["lo_shift"] * step - s["doppler_hz"]) <= step
+    finally:
+        acq.close()
+
+
+def test_grid_agrees_with_ref_mode_on_the_capture(ga, engines_ref=None):
+    """on the Nottingham capture GRID (1 ms, 500 Hz) finds the strong SVs of REF mode at
+    the same code phase (+-1 sample) and within one 500 Hz step."""
+    c = CAPTURES["nottingham"]
+    data = c["bin"].read_bytes()
+    ref = np.load(c["peaks"])[:32]                       # run 0 of the reference (chunk k <-> PRN k+1)
+    acq = ga.Acquisition(c["fc"], c["fs"], 5000.0, mode=1, doppler_step=500.0, noncoh_blocks=1)
+    try:
+        for sv in (0, 28, 29, 30):                       # the strongest four
+            chunk = data[sv * 5120: sv * 5120 + 682]     # first 1 ms of that PRN's REF chunk
+            p = acq.acquire(chunk)[sv]
+            assert abs(int(p["ca_shift"]) - int(ref[sv]["ca_shift"])) <= 1
+            assert abs(p["lo_shift"] * 500.0 - ref[sv]["lo_shift"] * c["fs"] / 40000) <= 500.0
+            assert p["snr"] >= 25
+    finally:
+        acq.close()
+
+
+def test_grid_rejects_bad_configs(ga):
+    with pytest.raises(ga.GpsAcqError, match="integer"):
+        ga.Acquisition(4.092e6, 5.456e6, 5000.0, mode=1, doppler_step=333.0)
+    acq = ga.Acquisition(4.092e6, 5.456e6, 5000.0, mode=1, doppler_step=500.0)
+    try:
+        with pytest.raises(ga.GpsAcqError, match="MODE_REF"):
+            acq.search_blocks(bytes(5120))
+        assert len(acq.acquire(b"")) == 0
+    finally:
+        acq.close()
+    ref = ga.Acquisition(4.092e6, 5.456e6)
+    try:
+        with pytest.raises(ga.GpsAcqError, match="MODE_GRID"):
+            ref.acquire(bytes(682))
+    finally:
+        ref.close()
