@@ -53,10 +53,19 @@ template <int DIR> struct Radix<2, DIR> {
 template <int DIR> struct Radix<4, DIR> {
     static GA_HD void run(cf (&x)[4])
     {
+#if defined(GA_R4_SCALAR) && GA_PACKED
+        // experiment: scalar adds (can issue on the fmalite pipe) instead of FADD2 (fmaheavy only)
+        const cf s0 = mk(x[0].x + x[2].x, x[0].y + x[2].y), d0 = mk(x[0].x - x[2].x, x[0].y - x[2].y);
+        const cf s1 = mk(x[1].x + x[3].x, x[1].y + x[3].y), d1 = mk(x[1].x - x[3].x, x[1].y - x[3].y);
+        x[0] = mk(s0.x + s1.x, s0.y + s1.y); x[2] = mk(s0.x - s1.x, s0.y - s1.y);
+        if (DIR > 0) { x[1] = mk(d0.x - d1.y, d0.y + d1.x); x[3] = mk(d0.x + d1.y, d0.y - d1.x); }
+        else         { x[1] = mk(d0.x + d1.y, d0.y - d1.x); x[3] = mk(d0.x - d1.y, d0.y + d1.x); }
+#else
         const cf s0 = cadd(x[0], x[2]), d0 = csub(x[0], x[2]);
         const cf s1 = cadd(x[1], x[3]), d1 = csub(x[1], x[3]);
         x[0] = cadd(s0, s1); x[1] = cadd_i<DIR>(d0, d1);     // d0 + DIR*i*d1
         x[2] = csub(s0, s1); x[3] = csub_i<DIR>(d0, d1);
+#endif
     }
 };
 
