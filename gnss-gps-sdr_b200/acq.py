@@ -71,6 +71,7 @@ def load_library() -> C.CDLL:
         "gpsacq_search_blocks_device": (C.c_int, [vp, vp, C.c_size_t, vp, vp]),
         "gpsacq_acquire": (C.c_int, [vp, vp, C.c_size_t, vp]),
         "gpsacq_acquire_device": (C.c_int, [vp, vp, C.c_size_t, vp]),
+        "gpsacq_iq8_to_bits": (C.c_int, [vp, vp, C.c_size_t, C.c_int, C.c_double, C.c_double, vp]),
         "gpsacq_stage_times": (C.c_int, [vp, f32p]),
         "gpsacq_get_replica_time": (C.c_int, [vp, C.c_int, vp]),
         "gpsacq_get_replica_spectrum": (C.c_int, [vp, C.c_int, vp]),
@@ -86,7 +87,7 @@ def load_library() -> C.CDLL:
 
 ABI_SYMBOLS = ("gpsacq_create", "gpsacq_destroy", "gpsacq_last_error", "gpsacq_get_info",
                "gpsacq_set_stream", "gpsacq_synchronize", "gpsacq_search_blocks",
-               "gpsacq_search_blocks_device", "gpsacq_acquire", "gpsacq_acquire_device", "gpsacq_stage_times", "gpsacq_get_replica_time",
+               "gpsacq_search_blocks_device", "gpsacq_acquire", "gpsacq_acquire_device", "gpsacq_iq8_to_bits", "gpsacq_stage_times", "gpsacq_get_replica_time",
                "gpsacq_get_replica_spectrum", "gpsacq_get_block_spectrum", "gpsacq_get_cell_stats")
 
 
@@ -180,6 +181,17 @@ class Acquisition:
 
     def acquire_device(self, d_bits_ptr: int, n_acq: int, d_out_ptr: int):
         self._check(self._lib.gpsacq_acquire_device(self._h, d_bits_ptr, n_acq, d_out_ptr))
+
+    # -- 8-bit IQ front-end (proc_rtl_bin_for_gps.m / proc_hackrf_bin_for_gps.m on the GPU) ----------------
+    def iq8_to_bits(self, iq, shift_hz: float, fs: float | None = None, signed: bool = False) -> np.ndarray:
+        """Interleaved I,Q bytes (uint8 offset-128 for rtl-sdr, int8 when `signed`) -> mean removal ->
+        shift up by shift_hz -> real part -> packed 1-bit samples (LSB first)."""
+        buf = np.ascontiguousarray(np.frombuffer(iq, dtype=np.uint8) if not isinstance(iq, np.ndarray) else iq.view(np.uint8))
+        n = buf.size // 2
+        out = np.zeros((n + 7) // 8, np.uint8)
+        self._check(self._lib.gpsacq_iq8_to_bits(self._h, buf.ctypes.data, n, 1 if signed else 0, shift_hz,
+                                                 fs if fs is not None else self.fs, out.ctypes.data))
+        return out
 
     def search_blocks_device(self, d_bits_ptr: int, n_blocks: int, d_sv_ptr: int | None, d_out_ptr: int):
         """Asynchronous device-pointer variant (raw CUDA device addresses)."""

@@ -21,6 +21,7 @@
 #define TM_MINB CELL_MINB
 #include "ga_kernels.cuh"
 #include "ga_grid.cuh"
+#include "ga_frontend.cuh"
 #include "ga_tables.h"
 
 using namespace ga;
@@ -106,6 +107,9 @@ struct gpsacq {
 #define CELL_MAXREG 144      // 2 CTAs x 7 warps x 32 lanes x 144 regs <= 64K registers per SM
 #endif
 
+#ifndef GA_CELL_PIPE
+#define GA_CELL_PIPE 0       // (experiment, slower: spills) prefetch the next sub-sequence's operands behind the barriers (cell_kernel_tm2)
+#endif
 #ifndef GA_CELL_TMEM
 #define GA_CELL_TMEM 1       // accumulators in tensor memory (cell_kernel_tm); 0 = registers (cell_kernel)
 #endif
@@ -114,6 +118,9 @@ template <class G, int T, int NW, int GID> struct CellKernel {
     static auto get()
     {
         if constexpr (G::ROT) return cell_kernel_rot<G, T, NW, CELL_MAXREG, GID>;   // experimental 2-barrier kernel
+        else if constexpr (GA_CELL_TMEM != 0 && GA_CELL_PIPE != 0 && T % 32 == 0 && G::RA == 20 && G::NA == G::NB &&
+                           G::NB == G::NC && cdiv(G::NA, 32) <= T / 32 && 2 * NW <= 32)
+            return cell_kernel_tm2<G, T, NW, GID>;       // software-pipelined operand prefetch
         else if constexpr (GA_CELL_TMEM != 0 && T % 32 == 0) return cell_kernel_tm<G, T, NW, GID>;
         else return cell_kernel<G, T, NW, CELL_MINB, GID>;
     }
@@ -124,13 +131,8 @@ static int launch_cells_t(gpsacq *h, size_t n_blocks, const int *d_sv)
 {
     const int n_cells = (int)(n_blocks * (size_t)h->ndop);
     const int grid = std::min(n_cells, h->cell_ctas);
-    if constexpr (GA_CELL_TMEM != 0 && !G::ROT && T % 32 == 0) {
-        cell_kernel_tm<G, T, NW, GID><<<grid, T, h->cell_smem, h->stream>>>(
-            h->d_xd, h->d_cext, d_sv, h->d_tw, n_cells, h->ndop, h->dmax, h->w, h->d_cells);
-    } else {
-        CellKernel<G, T, NW, GID>::get()<<<grid, T, h->cell_smem, h->stream>>>(
-            h->d_xd, h->d_cext, d_sv, h->d_tw, n_cells, h->ndop, h->dmax, h->w, h->d_cells);
-    }
+    CellKernel<G, T, NW, GID>::get()<<<grid, T, h->cell_smem, h->stream>>>(
+        h->d_xd, h->d_cext, d_sv, h->d_tw, n_cells, h->ndop, h->dmax, h->w, h->d_cells);
     CUDA_TRY(h, cudaGetLastError());
     return 0;
 }
@@ -654,6 +656,48 @@ int gpsacq_acquire(gpsacq_t *h, const uint8_t *bits, size_t n_acq, gpsacq_peak *
         done += na;
     }
     return GPSACQ_OK;
+}
+
+int gpsacq_iq8_to_bits(gpsacq_t *h, const void *iq, size_t n_samples, int format, double shift_hz, double fs, uint8_t *bits_out)
+{
+    if (!h || (!iq && n_samples) || (!bits_out && n_samples) || (format != GPSACQ_IQ_U8 && format != GPSACQ_IQ_S8) || !(fs > 0))
+        return GPSACQ_EINVAL;
+    if (n_samples == 0) return GPSACQ_OK;
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    const size_t piece = (size_t)1 << 26;                        // complex samples per device buffer (128 MB of IQ)
+    const size_t cap = std::min(piece, n_samples);
+    unsigned char *d_iq = nullptr, *d_bits = nullptr;
+    long long *d_sums = nullptr, sums[2] = {0, 0};
+    int rc = GPSACQ_OK;
+    do {
+        if (cudaMalloc(&d_iq, 2 * cap) != cudaSuccess || cudaMalloc(&d_bits, (cap + 7) / 8) != cudaSuccess ||
+            cudaMalloc(&d_sums, 2 * sizeof(long long)) != cudaSuccess) { h->err = "front-end: device allocation failed"; rc = GPSACQ_ENOMEM; break; }
+        if (cudaMemsetAsync(d_sums, 0, 2 * sizeof(long long), h->stream) != cudaSuccess) { rc = GPSACQ_ECUDA; break; }
+        // pass 1: mean over the whole capture (exact integer sums)
+        for (size_t done = 0; done < n_samples && rc == GPSACQ_OK; done += cap) {
+            const size_t n = std::min(cap, n_samples - done);
+            if (cudaMemcpyAsync(d_iq, (const unsigned char *)iq + 2 * done, 2 * n, cudaMemcpyHostToDevice, h->stream) != cudaSuccess) { rc = GPSACQ_ECUDA; break; }
+            iq8_sum_kernel<<<h->sm_count * 8, 256, 0, h->stream>>>(d_iq, n, format, d_sums);
+            if (n_samples > cap && cudaStreamSynchronize(h->stream) != cudaSuccess) { rc = GPSACQ_ECUDA; break; }
+        }
+        if (rc) break;
+        if (cudaMemcpyAsync(sums, d_sums, sizeof sums, cudaMemcpyDeviceToHost, h->stream) != cudaSuccess ||
+            cudaStreamSynchronize(h->stream) != cudaSuccess) { rc = GPSACQ_ECUDA; break; }
+        const double mi = (double)sums[0] / (double)n_samples, mq = (double)sums[1] / (double)n_samples;
+        // pass 2: shift, real part, sign, pack
+        for (size_t done = 0; done < n_samples; done += cap) {
+            const size_t n = std::min(cap, n_samples - done);
+            if (n_samples > cap || done > 0)
+                if (cudaMemcpyAsync(d_iq, (const unsigned char *)iq + 2 * done, 2 * n, cudaMemcpyHostToDevice, h->stream) != cudaSuccess) { rc = GPSACQ_ECUDA; break; }
+            const size_t nbytes = (n + 7) / 8;
+            iq8_to_bits_kernel<<<(unsigned)((nbytes + 255) / 256), 256, 0, h->stream>>>(d_iq, n, done, format, mi, mq, shift_hz, fs, d_bits);
+            if (cudaMemcpyAsync(bits_out + done / 8, d_bits, nbytes, cudaMemcpyDeviceToHost, h->stream) != cudaSuccess ||
+                cudaStreamSynchronize(h->stream) != cudaSuccess) { rc = GPSACQ_ECUDA; break; }
+        }
+    } while (0);
+    if (rc == GPSACQ_ECUDA) h->err = std::string("front-end: ") + cudaGetErrorString(cudaGetLastError());
+    cudaFree(d_iq); cudaFree(d_bits); cudaFree(d_sums);
+    return rc;
 }
 
 int gpsacq_stage_times(gpsacq_t *h, float ms[4])

@@ -78,3 +78,24 @@ def default_constellation(fs: float, cn0_dbhz: float = 45.0, seed: int = 1575420
     return [dict(prn=p, doppler_hz=float(rng.uniform(-max_doppler, max_doppler)),
                  code_phase_chips=float(rng.uniform(0, 1023)), amp=amp)
             for p in (1, 5, 8, 13, 21, 29, 30, 31)]
+
+
+def synth_iq8(n_samples: int, fs: float, sats, seed: int = 7, noise_sigma: float = 20.0, dc=(3.3, -2.1),
+              signed: bool = False, nav_bps: float = 50.0) -> np.ndarray:
+    """Interleaved 8-bit IQ baseband capture as an rtl-sdr (uint8, offset 128) or a HackRF (int8) writes
+    it: the receiver is tuned to L1, so satellite k sits at its Doppler.  A DC offset is added because
+    real dongles have one -- that is what the `y - mean(y)` of proc_rtl_bin_for_gps.m:36 removes."""
+    rng = np.random.default_rng(seed)
+    sats = list(sats)
+    t = np.arange(n_samples, dtype=np.float64) / fs
+    y = noise_sigma * (rng.standard_normal(n_samples) + 1j * rng.standard_normal(n_samples)) + complex(*dc)
+    nbits = int(np.ceil(n_samples / fs * nav_bps)) + 2
+    for s in sats:
+        code = 1.0 - 2.0 * cacode(s["prn"]).astype(np.float64)
+        chip = (t * (CPS * (1.0 + s["doppler_hz"] / 1575.42e6)) + s["code_phase_chips"]) % 1023.0
+        d = (1.0 - 2.0 * rng.integers(0, 2, nbits))[(t * nav_bps).astype(np.int64)]
+        y += s["amp"] * noise_sigma * d * code[chip.astype(np.int64)] * np.exp(1j * (2 * np.pi * s["doppler_hz"] * t + rng.uniform(0, 2 * np.pi)))
+    iq = np.empty(2 * n_samples, np.float64)
+    iq[0::2], iq[1::2] = np.round(y.real), np.round(y.imag)
+    iq = np.clip(iq, -127, 127)
+    return iq.astype(np.int8).view(np.uint8) if signed else (iq + 128).astype(np.uint8)

@@ -162,6 +162,17 @@ int  gpsacq_search_blocks_device(gpsacq_t *h, const uint8_t *d_packed_bits, size
 int  gpsacq_acquire(gpsacq_t *h, const uint8_t *packed_bits, size_t n_acq, gpsacq_peak *out);
 int  gpsacq_acquire_device(gpsacq_t *h, const uint8_t *d_packed_bits, size_t n_acq, gpsacq_peak *d_out);
 
+/* 8-bit IQ front-end (replaces the MATLAB step of the reference's SDR workflows,
+ * proc_rtl_bin_for_gps.m:31-47 / proc_hackrf_bin_for_gps.m:7-19): interleaved I,Q bytes ->
+ * remove the capture's mean -> shift up by shift_hz (the IF that gps_test is then told, e.g. 0.62e6)
+ * -> take the real part -> 1 bit per sample, packed LSB first, ready for gpsacq_search_blocks() /
+ * gpsacq_acquire().  format: GPSACQ_IQ_U8 (rtl-sdr, offset 128) or GPSACQ_IQ_S8 (HackRF).  n_samples
+ * complex samples in, ceil(n_samples/8) bytes out.  Host buffers; runs on the handle's device. */
+#define GPSACQ_IQ_U8 0
+#define GPSACQ_IQ_S8 1
+int  gpsacq_iq8_to_bits(gpsacq_t *h, const void *iq, size_t n_samples, int format, double shift_hz,
+                        double fs, uint8_t *bits_out);
+
 /* Elapsed milliseconds of the stages of the most recent batch, measured with CUDA
  * events on the launching stream: [0] unpack+mix+forward FFT kernel, [1] cell kernel
  * (conj-multiply + backward FFT + peak), [2] best-over-Doppler kernel, [3] whole batch.

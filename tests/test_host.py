@@ -19,7 +19,7 @@ def built():
 
 def test_c_abi_exports_every_declared_symbol(ga):
     header = (ROOT / "include" / "gpsacq.h").read_text()
-    declared = set(re.findall(r"\b(gpsacq_[a-z_]+)\s*\(", header))
+    declared = set(re.findall(r"\b(gpsacq_[a-z0-9_]+)\s*\(", header))
     declared -= {"gpsacq_cfg", "gpsacq_peak", "gpsacq_cell", "gpsacq_info"}
     lib = ctypes.CDLL(str(ga.lib_path()))
     for name in sorted(declared):
