@@ -316,6 +316,8 @@ def run_engine(args, rank, world, local_rank):
                 "clocks": clocks,
                 "stage_ms": {k: round(v, 4) for k, v in stage.items()},
                 "detected_prns_last_step": detected}
+        if world == 1 and not args.no_grid:
+            line["grid_mode_configs1"] = grid_c1_measure(ga, dev, peak_gbs)
         if world == 1 and not args.no_cpu_baseline:
             cb, _, _ = cpu_baseline(runs_per_core=4)
             os.unlink(cpu_sample_file())
@@ -324,6 +326,39 @@ def run_engine(args, rank, world, local_rank):
     acq.close()
     if world > 1:
         dist.destroy_process_group()
+
+
+def grid_c1_measure(ga, dev, peak_gbs):
+    """Secondary, informational: BASELINE.json configs[1] in GRID semantics (1 ms coherent, +-5 kHz @ 500 Hz,
+    21 bins, all 32 PRNs on the same block) -- a mode the reference does not have (no reference arm, parity
+    against the oracle's definition only).  64 acquisitions per launch, device-resident, CUDA events."""
+    import importlib
+    import torch
+    sg = importlib.import_module("gnss_gps_sdr_b200.siggen")
+    n_acq, W = 64, 5456
+    bits = sg.synth_capture(W * n_acq, FS, FC, sg.default_constellation(FS, seed=1575420000), seed=3)
+    acq = ga.Acquisition(FC, FS, MAX_FO, device=dev.index, mode=1, doppler_step=500.0, noncoh_blocks=1, max_blocks=n_acq)
+    d_bits = torch.from_numpy(bits).to(dev)
+    d_out = torch.zeros(n_acq * 32 * 32, dtype=torch.uint8, device=dev)
+    stream = torch.cuda.current_stream(dev)
+    acq.set_stream(stream.cuda_stream)
+    for _ in range(3):
+        acq.acquire_device(d_bits.data_ptr(), n_acq, d_out.data_ptr())
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(20):
+        acq.acquire_device(d_bits.data_ptr(), n_acq, d_out.data_ptr())
+    e1.record(stream)
+    torch.cuda.synchronize(dev)
+    ms = e0.elapsed_time(e1) / 20
+    corr = n_acq * 32 * acq.n_doppler
+    bpc = acq.info["bytes_per_corr"]
+    out = {"workload": "GRID C1: fs=5.456MHz, 32 PRN x 21 bins (+-5 kHz @ 500 Hz), 1 ms coherent, 64 acquisitions per launch",
+           "value": corr / ms * 1e3, "unit": UNIT, "ms_per_launch": ms, "bytes_per_corr": bpc,
+           "contract_gbs": corr * bpc / ms / 1e6, "frac_of_hbm_peak": corr * bpc / ms / 1e6 / peak_gbs,
+           "note": "computed through a zero-padded 16000-point embedding of the 5456-point correlation (DESIGN.md section 10)"}
+    acq.close()
+    return out
 
 
 def ga_launches(steps: int) -> int:
@@ -337,6 +372,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-grid", action="store_true")
     ap.add_argument("--cpu-worker")
     ap.add_argument("--cpu-kind", default="reference")
     ap.add_argument("--cpu-runs", type=int, default=2)

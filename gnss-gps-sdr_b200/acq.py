@@ -72,6 +72,12 @@ def load_library() -> C.CDLL:
         "gpsacq_acquire": (C.c_int, [vp, vp, C.c_size_t, vp]),
         "gpsacq_acquire_device": (C.c_int, [vp, vp, C.c_size_t, vp]),
         "gpsacq_iq8_to_bits": (C.c_int, [vp, vp, C.c_size_t, C.c_int, C.c_double, C.c_double, vp]),
+        "gpsacq_group_create": (C.c_int, [C.POINTER(_Cfg), C.c_int, i32p, C.c_int, C.POINTER(vp)]),
+        "gpsacq_group_destroy": (None, [vp]),
+        "gpsacq_group_search_blocks": (C.c_int, [vp, vp, C.c_size_t, vp]),
+        "gpsacq_group_gather_kind": (C.c_char_p, [vp]),
+        "gpsacq_group_last_error": (C.c_char_p, [vp]),
+        "gpsacq_group_engine": (vp, [vp, C.c_int]),
         "gpsacq_stage_times": (C.c_int, [vp, f32p]),
         "gpsacq_get_replica_time": (C.c_int, [vp, C.c_int, vp]),
         "gpsacq_get_replica_spectrum": (C.c_int, [vp, C.c_int, vp]),
@@ -87,7 +93,9 @@ def load_library() -> C.CDLL:
 
 ABI_SYMBOLS = ("gpsacq_create", "gpsacq_destroy", "gpsacq_last_error", "gpsacq_get_info",
                "gpsacq_set_stream", "gpsacq_synchronize", "gpsacq_search_blocks",
-               "gpsacq_search_blocks_device", "gpsacq_acquire", "gpsacq_acquire_device", "gpsacq_iq8_to_bits", "gpsacq_stage_times", "gpsacq_get_replica_time",
+               "gpsacq_search_blocks_device", "gpsacq_acquire", "gpsacq_acquire_device", "gpsacq_iq8_to_bits", "gpsacq_group_create",
+               "gpsacq_group_destroy", "gpsacq_group_search_blocks", "gpsacq_group_gather_kind", "gpsacq_group_last_error",
+               "gpsacq_group_engine", "gpsacq_stage_times", "gpsacq_get_replica_time",
                "gpsacq_get_replica_spectrum", "gpsacq_get_block_spectrum", "gpsacq_get_cell_stats")
 
 
@@ -228,6 +236,43 @@ class Acquisition:
         out = np.zeros(self.n_doppler, CELL_DTYPE)
         self._check(self._lib.gpsacq_get_cell_stats(self._h, block, out.ctypes.data))
         return out
+
+
+class AcquisitionGroup:
+    """Several GPUs in one process (REF mode): contiguous chunk ranges per device, one ncclAllGather of the
+    peak records per batch (include/gpsacq.h, gpsacq_group_*)."""
+
+    def __init__(self, fc: float, fs: float, max_fo: float = 5000.0, n_gpus: int = 2, use_nccl: bool = True, max_blocks: int = 0):
+        self._lib = load_library()
+        self._g = C.c_void_p()
+        cfg = _Cfg(fc=fc, fs=fs, max_fo=max_fo, fft_len=0, device=-1, max_blocks=max_blocks, mode=0, doppler_step=0.0,
+                   noncoh_blocks=1, reserved=0)
+        rc = self._lib.gpsacq_group_create(C.byref(cfg), n_gpus, None, 1 if use_nccl else 0, C.byref(self._g))
+        if rc != 0:
+            msg = self._lib.gpsacq_last_error(None)
+            raise GpsAcqError(f"gpsacq_group_create failed ({rc}): {msg.decode() if msg else '?'}")
+        self.gather_kind = self._lib.gpsacq_group_gather_kind(self._g).decode()
+        self.chunk_bytes = 5120
+
+    def search_blocks(self, bits) -> np.ndarray:
+        buf = np.ascontiguousarray(np.frombuffer(bits, dtype=np.uint8) if not isinstance(bits, np.ndarray) else bits, dtype=np.uint8)
+        n = buf.size // self.chunk_bytes
+        out = np.zeros(n, dtype=PEAK_DTYPE)
+        rc = self._lib.gpsacq_group_search_blocks(self._g, buf.ctypes.data, n, out.ctypes.data)
+        if rc != 0:
+            raise GpsAcqError(f"group search failed ({rc}): {self._lib.gpsacq_group_last_error(self._g).decode()}")
+        return out
+
+    def close(self):
+        if self._g and self._g.value:
+            self._lib.gpsacq_group_destroy(self._g)
+            self._g = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 # ---- SearchTask() report formatting (c/search_offline.cpp:264-287) -------------------------

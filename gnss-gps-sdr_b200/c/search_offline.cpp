@@ -10,13 +10,14 @@
 //   * "can not open file!" on fopen failure (:224-228)
 // Optional environment knobs (absent = reference behaviour):
 //   GPSACQ_DEVICE=<ordinal>      first CUDA device to use (default 0)
-//   GPSACQ_GPUS=<n>              shard each batch's chunks over n GPUs (default 1)
+//   GPSACQ_GPUS=<n>              shard each batch's chunks over n GPUs (default 1); the 32-byte peak
+//                                records come back with one ncclAllGather per batch (GPSACQ_GATHER=host
+//                                gathers through host memory instead)
 //   GPSACQ_RUNS_PER_BATCH=<r>    runs handed to the GPU per call (default 16)
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
 #include <vector>
-#include <thread>
 
 #include "gps_offline.h"
 #include "cacode.h"
@@ -34,7 +35,7 @@ const SatTap kSats[NUM_SATS] = {
 };
 
 bool g_busy[NUM_SATS];
-std::vector<gpsacq_t *> g_engines;        // one per GPU
+gpsacq_group_t *g_group = NULL;           // one engine per GPU + the peak-record gather (NCCL or host)
 int g_chunk_bytes = 0;
 int g_runs_per_batch = 16;
 
@@ -42,28 +43,6 @@ int env_int(const char *name, int dflt)
 {
     const char *v = getenv(name);
     return (v && *v) ? atoi(v) : dflt;
-}
-
-// search n_blocks chunks (block b -> PRN (b mod 32)+1), sharded contiguously over the engines
-int search_batch(const unsigned char *bits, size_t n_blocks, gpsacq_peak *out)
-{
-    const size_t ng = g_engines.size();
-    if (ng == 1) return gpsacq_search_blocks(g_engines[0], bits, n_blocks, NULL, out);
-    std::vector<int> rc(ng, 0);
-    std::vector<std::thread> th;
-    std::vector<std::vector<int32_t> > svs(ng);
-    for (size_t g = 0; g < ng; g++) {
-        const size_t lo = n_blocks * g / ng, hi = n_blocks * (g + 1) / ng;
-        svs[g].resize(hi - lo);
-        for (size_t b = lo; b < hi; b++) svs[g][b - lo] = (int32_t)(b % NUM_SATS);
-        th.emplace_back([&, g, lo, hi]() {
-            rc[g] = gpsacq_search_blocks(g_engines[g], bits + lo * (size_t)g_chunk_bytes, hi - lo,
-                                         svs[g].data(), out + lo);
-        });
-    }
-    for (auto &t : th) t.join();
-    for (size_t g = 0; g < ng; g++) if (rc[g]) return rc[g];
-    return 0;
 }
 
 void print_run(int run_count, const gpsacq_peak *pk)
@@ -93,32 +72,32 @@ int SearchInit()
     if (ngpu < 1) ngpu = 1;
     g_runs_per_batch = env_int("GPSACQ_RUNS_PER_BATCH", 16);
     if (g_runs_per_batch < 1) g_runs_per_batch = 1;
-    for (int g = 0; g < ngpu; g++) {
-        gpsacq_cfg cfg;
-        memset(&cfg, 0, sizeof cfg);
-        cfg.fc = FC; cfg.fs = FS; cfg.max_fo = max_fo;
-        cfg.fft_len = FFT_LEN;
-        cfg.device = first + g;
-        cfg.max_blocks = g_runs_per_batch * NUM_SATS;
-        gpsacq_t *h = NULL;
-        const int rc = gpsacq_create(&cfg, &h);
-        if (rc != GPSACQ_OK) {
-            fprintf(stderr, "gpsacq_create(device %d): %s\n", cfg.device, gpsacq_last_error(NULL));
-            SearchFree();
-            return rc;
-        }
-        g_engines.push_back(h);
+    const char *gather = getenv("GPSACQ_GATHER");
+    gpsacq_cfg cfg;
+    memset(&cfg, 0, sizeof cfg);
+    cfg.fc = FC; cfg.fs = FS; cfg.max_fo = max_fo;
+    cfg.fft_len = FFT_LEN;
+    cfg.mode = GPSACQ_MODE_REF;
+    cfg.max_blocks = g_runs_per_batch * NUM_SATS;      // per GPU
+    std::vector<int32_t> devs(ngpu);
+    for (int g = 0; g < ngpu; g++) devs[g] = first + g;
+    const int rc = gpsacq_group_create(&cfg, ngpu, devs.data(), !(gather && strcmp(gather, "host") == 0), &g_group);
+    if (rc != GPSACQ_OK) {
+        fprintf(stderr, "gpsacq_group_create: %s\n", gpsacq_last_error(NULL));
+        g_group = NULL;
+        return rc;
     }
+    g_runs_per_batch *= ngpu;                           // a host batch feeds every GPU a full share
     gpsacq_info info;
-    gpsacq_get_info(g_engines[0], &info);
+    gpsacq_get_info(gpsacq_group_engine(g_group, 0), &info);
     g_chunk_bytes = info.chunk_bytes;
     return 0;
 }
 
 void SearchFree()
 {
-    for (size_t g = 0; g < g_engines.size(); g++) gpsacq_destroy(g_engines[g]);
-    g_engines.clear();
+    if (g_group) gpsacq_group_destroy(g_group);
+    g_group = NULL;
 }
 
 void SearchEnable(int sv)
@@ -141,7 +120,7 @@ void SearchTask(char *filename_1bit_bin)
 {
     FILE *fp = fopen(filename_1bit_bin, "rb");
     if (!fp) { printf("can not open file!\n"); return; }
-    if (g_engines.empty()) { fclose(fp); fprintf(stderr, "SearchTask: SearchInit() has not succeeded\n"); return; }
+    if (!g_group) { fclose(fp); fprintf(stderr, "SearchTask: SearchInit() has not succeeded\n"); return; }
 
     const size_t run_bytes = (size_t)NUM_SATS * g_chunk_bytes;
     std::vector<unsigned char> buf(run_bytes * g_runs_per_batch);
@@ -151,8 +130,8 @@ void SearchTask(char *filename_1bit_bin)
         const size_t got = fread(buf.data(), 1, buf.size(), fp);
         const size_t full_runs = got / run_bytes;
         if (full_runs) {
-            const int rc = search_batch(buf.data(), full_runs * NUM_SATS, peaks.data());
-            if (rc) { fprintf(stderr, "gpsacq_search_blocks: %s\n", gpsacq_last_error(g_engines[0])); break; }
+            const int rc = gpsacq_group_search_blocks(g_group, buf.data(), full_runs * NUM_SATS, peaks.data());
+            if (rc) { fprintf(stderr, "gpsacq_group_search_blocks: %s\n", gpsacq_group_last_error(g_group)); break; }
             for (size_t r = 0; r < full_runs; r++) print_run(run_count++, &peaks[r * NUM_SATS]);
         }
         if (got < buf.size()) { printf("run out of file!\n"); break; }

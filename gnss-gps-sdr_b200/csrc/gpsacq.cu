@@ -758,3 +758,156 @@ int gpsacq_get_cell_stats(gpsacq_t *h, size_t blk, gpsacq_cell *out)
 }
 
 }  // extern "C"
+
+// =========================================================================================
+// Several GPUs in one process: contiguous chunk ranges per device + one ncclAllGather of peak records
+// =========================================================================================
+#include <dlfcn.h>
+typedef struct ncclComm *ncclComm_t;
+typedef int ncclResult_t;
+struct NcclApi {
+    void *lib;
+    ncclResult_t (*CommInitAll)(ncclComm_t *, int, const int *);
+    ncclResult_t (*CommDestroy)(ncclComm_t);
+    ncclResult_t (*GroupStart)();
+    ncclResult_t (*GroupEnd)();
+    ncclResult_t (*AllGather)(const void *, void *, size_t, int /*ncclDataType_t*/, ncclComm_t, cudaStream_t);
+    const char *(*GetErrorString)(ncclResult_t);
+    bool ok;
+};
+static bool nccl_load(NcclApi &a)
+{
+    memset(&a, 0, sizeof a);
+    const char *names[] = {"libnccl.so.2", "libnccl.so"};
+    for (const char *n : names) { a.lib = dlopen(n, RTLD_NOW | RTLD_GLOBAL); if (a.lib) break; }
+    if (!a.lib) return false;
+    a.CommInitAll = (decltype(a.CommInitAll))dlsym(a.lib, "ncclCommInitAll");
+    a.CommDestroy = (decltype(a.CommDestroy))dlsym(a.lib, "ncclCommDestroy");
+    a.GroupStart = (decltype(a.GroupStart))dlsym(a.lib, "ncclGroupStart");
+    a.GroupEnd = (decltype(a.GroupEnd))dlsym(a.lib, "ncclGroupEnd");
+    a.AllGather = (decltype(a.AllGather))dlsym(a.lib, "ncclAllGather");
+    a.GetErrorString = (decltype(a.GetErrorString))dlsym(a.lib, "ncclGetErrorString");
+    a.ok = a.CommInitAll && a.CommDestroy && a.GroupStart && a.GroupEnd && a.AllGather;
+    return a.ok;
+}
+
+struct gpsacq_group {
+    std::vector<gpsacq *> eng;
+    std::vector<int> dev;
+    std::vector<ncclComm_t> comm;
+    std::vector<Peak *> d_all;        // per device: n_gpus * cap records
+    std::vector<std::vector<int> > sv;
+    NcclApi nccl;
+    bool use_nccl;
+    int cap;                          // per-device share of a batch
+    std::vector<Peak> h_all;
+    std::string err;
+};
+
+extern "C" {
+
+const char *gpsacq_group_last_error(const gpsacq_group_t *g) { return g ? g->err.c_str() : g_create_error.c_str(); }
+const char *gpsacq_group_gather_kind(const gpsacq_group_t *g) { return (g && g->use_nccl) ? "nccl" : "host"; }
+gpsacq_t *gpsacq_group_engine(gpsacq_group_t *g, int i) { return (g && i >= 0 && i < (int)g->eng.size()) ? g->eng[i] : nullptr; }
+
+void gpsacq_group_destroy(gpsacq_group_t *g)
+{
+    if (!g) return;
+    for (size_t i = 0; i < g->eng.size(); i++) {
+        cudaSetDevice(g->dev[i]);
+        if (i < g->d_all.size()) cudaFree(g->d_all[i]);
+        if (g->use_nccl && i < g->comm.size() && g->comm[i]) g->nccl.CommDestroy(g->comm[i]);
+        gpsacq_destroy(g->eng[i]);
+    }
+    delete g;
+}
+
+int gpsacq_group_create(const gpsacq_cfg *cfg, int n_gpus, const int32_t *devices, int use_nccl, gpsacq_group_t **out)
+{
+    if (!cfg || !out || n_gpus < 1 || cfg->mode != GPSACQ_MODE_REF) { g_create_error = "gpsacq_group_create: bad arguments (REF mode only)"; return GPSACQ_EINVAL; }
+    *out = nullptr;
+    gpsacq_group *g = new (std::nothrow) gpsacq_group();
+    if (!g) return GPSACQ_ENOMEM;
+    g->use_nccl = false;
+    for (int i = 0; i < n_gpus; i++) {
+        gpsacq_cfg c = *cfg;
+        c.device = devices ? devices[i] : i;
+        gpsacq *h = nullptr;
+        const int rc = gpsacq_create(&c, &h);
+        if (rc) { gpsacq_group_destroy(g); return rc; }
+        g->eng.push_back(h);
+        g->dev.push_back(h->device);
+    }
+    g->cap = g->eng[0]->cap;
+    g->sv.resize(n_gpus);
+    g->d_all.assign(n_gpus, nullptr);
+    for (int i = 0; i < n_gpus; i++) {
+        cudaSetDevice(g->dev[i]);
+        if (cudaMalloc(&g->d_all[i], (size_t)n_gpus * g->cap * sizeof(Peak)) != cudaSuccess) { g_create_error = "group: cudaMalloc failed"; gpsacq_group_destroy(g); return GPSACQ_ENOMEM; }
+    }
+    g->h_all.resize((size_t)n_gpus * g->cap);
+    if (use_nccl && n_gpus > 1 && nccl_load(g->nccl)) {
+        g->comm.assign(n_gpus, nullptr);
+        const ncclResult_t r = g->nccl.CommInitAll(g->comm.data(), n_gpus, g->dev.data());
+        if (r == 0) g->use_nccl = true;
+        else g->comm.clear();
+    }
+    *out = g;
+    return GPSACQ_OK;
+}
+
+int gpsacq_group_search_blocks(gpsacq_group_t *g, const uint8_t *bits, size_t n_blocks, gpsacq_peak *out)
+{
+    if (!g || (!bits && n_blocks) || (!out && n_blocks)) return GPSACQ_EINVAL;
+    const size_t ng = g->eng.size(), per_batch = (size_t)g->cap * ng;
+    for (size_t done = 0; done < n_blocks;) {
+        const size_t nb = std::min(per_batch, n_blocks - done);
+        // contiguous, balanced ranges of this batch; chunk b of the stream keeps PRN b mod 32
+        std::vector<size_t> lo(ng + 1);
+        for (size_t d = 0; d <= ng; d++) lo[d] = nb * d / ng;
+        for (size_t d = 0; d < ng; d++) {
+            gpsacq *h = g->eng[d];
+            const size_t n = lo[d + 1] - lo[d];
+            if (cudaSetDevice(h->device) != cudaSuccess) { g->err = "cudaSetDevice failed"; return GPSACQ_ECUDA; }
+            if (n == 0) continue;
+            memcpy(h->h_bits, bits + (done + lo[d]) * (size_t)h->chunk_bytes, n * (size_t)h->chunk_bytes);
+            for (size_t b = 0; b < n; b++) h->h_sv[b] = (int)((done + lo[d] + b) % GPSACQ_NUM_SATS);
+            if (cudaMemcpyAsync(h->d_bits, h->h_bits, n * (size_t)h->chunk_bytes, cudaMemcpyHostToDevice, h->stream) != cudaSuccess ||
+                cudaMemcpyAsync(h->d_sv, h->h_sv, n * sizeof(int), cudaMemcpyHostToDevice, h->stream) != cudaSuccess) { g->err = "H2D copy failed"; return GPSACQ_ECUDA; }
+            const int rc = gpsacq_search_blocks_device(h, h->d_bits, n, h->d_sv, (gpsacq_peak *)h->d_peaks);
+            if (rc) { g->err = h->err; return rc; }
+        }
+        if (g->use_nccl) {
+            // ONE collective per batch: every device ends up with every device's (padded) records
+            g->nccl.GroupStart();
+            for (size_t d = 0; d < ng; d++) {
+                cudaSetDevice(g->dev[d]);
+                g->nccl.AllGather(g->eng[d]->d_peaks, g->d_all[d], (size_t)g->cap * sizeof(Peak), 0 /*ncclInt8*/, g->comm[d], g->eng[d]->stream);
+            }
+            const ncclResult_t r = g->nccl.GroupEnd();
+            if (r != 0) { g->err = std::string("ncclAllGather: ") + (g->nccl.GetErrorString ? g->nccl.GetErrorString(r) : "error"); return GPSACQ_ECUDA; }
+            cudaSetDevice(g->dev[0]);
+            if (cudaMemcpyAsync(g->h_all.data(), g->d_all[0], ng * (size_t)g->cap * sizeof(Peak), cudaMemcpyDeviceToHost, g->eng[0]->stream) != cudaSuccess) { g->err = "D2H failed"; return GPSACQ_ECUDA; }
+            for (size_t d = 0; d < ng; d++) { cudaSetDevice(g->dev[d]); if (cudaStreamSynchronize(g->eng[d]->stream) != cudaSuccess) { g->err = "stream sync failed"; return GPSACQ_ECUDA; } }
+            for (size_t d = 0; d < ng; d++)
+                memcpy(out + done + lo[d], g->h_all.data() + d * (size_t)g->cap, (lo[d + 1] - lo[d]) * sizeof(Peak));
+        } else {
+            for (size_t d = 0; d < ng; d++) {
+                gpsacq *h = g->eng[d];
+                const size_t n = lo[d + 1] - lo[d];
+                cudaSetDevice(h->device);
+                if (n && cudaMemcpyAsync(h->h_peaks, h->d_peaks, n * sizeof(Peak), cudaMemcpyDeviceToHost, h->stream) != cudaSuccess) { g->err = "D2H failed"; return GPSACQ_ECUDA; }
+            }
+            for (size_t d = 0; d < ng; d++) {
+                gpsacq *h = g->eng[d];
+                cudaSetDevice(h->device);
+                if (cudaStreamSynchronize(h->stream) != cudaSuccess) { g->err = "stream sync failed"; return GPSACQ_ECUDA; }
+                memcpy(out + done + lo[d], h->h_peaks, (lo[d + 1] - lo[d]) * sizeof(Peak));
+            }
+        }
+        done += nb;
+    }
+    return GPSACQ_OK;
+}
+
+}  // extern "C" (group)

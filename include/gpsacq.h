@@ -173,6 +173,21 @@ int  gpsacq_acquire_device(gpsacq_t *h, const uint8_t *d_packed_bits, size_t n_a
 int  gpsacq_iq8_to_bits(gpsacq_t *h, const void *iq, size_t n_samples, int format, double shift_hz,
                         double fs, uint8_t *bits_out);
 
+/* ---- several GPUs in one process (REF mode) ----------------------------------------------------
+ * One engine per device; a batch's chunks are split into contiguous ranges (chunk b keeps PRN b mod 32),
+ * every device searches its range, and the 32-byte peak records are exchanged with ONE collective per
+ * batch: ncclAllGather over NVLink (NCCL is dlopen'ed -- libnccl.so.2 -- so the library has no link-time
+ * dependency on it; if it cannot be loaded, or use_nccl = 0, the records are gathered through the host).
+ * No collective touches the data path.  gpsacq_group_gather_kind() says which gather is active. */
+typedef struct gpsacq_group gpsacq_group_t;
+int  gpsacq_group_create(const gpsacq_cfg *cfg, int n_gpus, const int32_t *devices /* NULL: 0..n-1 */,
+                         int use_nccl, gpsacq_group_t **out);
+void gpsacq_group_destroy(gpsacq_group_t *g);
+int  gpsacq_group_search_blocks(gpsacq_group_t *g, const uint8_t *packed_bits, size_t n_blocks, gpsacq_peak *out);
+const char *gpsacq_group_gather_kind(const gpsacq_group_t *g);   /* "nccl" or "host" */
+const char *gpsacq_group_last_error(const gpsacq_group_t *g);
+gpsacq_t *gpsacq_group_engine(gpsacq_group_t *g, int i);         /* engine of the i-th device (for info/probes) */
+
 /* Elapsed milliseconds of the stages of the most recent batch, measured with CUDA
  * events on the launching stream: [0] unpack+mix+forward FFT kernel, [1] cell kernel
  * (conj-multiply + backward FFT + peak), [2] best-over-Doppler kernel, [3] whole batch.

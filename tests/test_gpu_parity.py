@@ -246,3 +246,21 @@ def test_device_api_on_torch_stream(ga, engines):
     assert got.tobytes() == host.tobytes()
     t = acq.stage_times()
     assert t["cells_ms"] > 0 and t["total_ms"] >= t["cells_ms"]
+
+
+# ---- several GPUs in one process: chunk ranges per device + ncclAllGather of the peak records ----------------
+@pytest.mark.parametrize("use_nccl", [True, False])
+def test_group_api_matches_single_gpu(ga, engines, use_nccl):
+    import torch
+    n = min(torch.cuda.device_count(), 2)
+    c = CAPTURES["nottingham"]
+    data = c["bin"].read_bytes()
+    base = engines(c["fc"], c["fs"]).search_blocks(data)
+    grp = ga.AcquisitionGroup(c["fc"], c["fs"], n_gpus=n, use_nccl=use_nccl, max_blocks=40)   # 128 chunks -> 2 batches
+    try:
+        assert grp.gather_kind == ("nccl" if (use_nccl and n > 1) else "host")
+        got = grp.search_blocks(data)
+        assert got.tobytes() == base.tobytes()
+        assert len(grp.search_blocks(data[: 3 * 5120])) == 3        # fewer chunks than GPUs*... ragged shares
+    finally:
+        grp.close()
