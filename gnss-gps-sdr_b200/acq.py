@@ -38,6 +38,11 @@ class _Info(C.Structure):
                 ("block_bytes", C.c_int32), ("max_acq", C.c_int32), ("doppler_step", C.c_double)]
 
 
+class _Sat(C.Structure):
+    _fields_ = [("prn", C.c_int32), ("reserved", C.c_int32), ("amp", C.c_double), ("doppler_hz", C.c_double),
+                ("code_phase_chips", C.c_double), ("carrier_phase_cycles", C.c_double)]
+
+
 PEAK_DTYPE = np.dtype([("snr", "<f4"), ("max_pwr", "<f4"), ("tot_pwr", "<f4"), ("lo_shift", "<i4"),
                        ("ca_shift", "<i4"), ("sv", "<i4"), ("flags", "<i4"), ("reserved", "<i4")])
 CELL_DTYPE = np.dtype([("max_pwr", "<f4"), ("tot_pwr", "<f4"), ("max_idx", "<i4"), ("reserved", "<i4")])
@@ -78,6 +83,8 @@ def load_library() -> C.CDLL:
         "gpsacq_group_gather_kind": (C.c_char_p, [vp]),
         "gpsacq_group_last_error": (C.c_char_p, [vp]),
         "gpsacq_group_engine": (vp, [vp, C.c_int]),
+        "gpsacq_synth_capture": (C.c_int, [C.c_int, C.c_double, C.c_double, C.POINTER(_Sat), C.c_int, C.c_double, C.c_double,
+                                           C.c_uint64, C.c_size_t, vp, vp]),
         "gpsacq_stage_times": (C.c_int, [vp, f32p]),
         "gpsacq_get_replica_time": (C.c_int, [vp, C.c_int, vp]),
         "gpsacq_get_replica_spectrum": (C.c_int, [vp, C.c_int, vp]),
@@ -95,7 +102,7 @@ ABI_SYMBOLS = ("gpsacq_create", "gpsacq_destroy", "gpsacq_last_error", "gpsacq_g
                "gpsacq_set_stream", "gpsacq_synchronize", "gpsacq_search_blocks",
                "gpsacq_search_blocks_device", "gpsacq_acquire", "gpsacq_acquire_device", "gpsacq_iq8_to_bits", "gpsacq_group_create",
                "gpsacq_group_destroy", "gpsacq_group_search_blocks", "gpsacq_group_gather_kind", "gpsacq_group_last_error",
-               "gpsacq_group_engine", "gpsacq_stage_times", "gpsacq_get_replica_time",
+               "gpsacq_group_engine", "gpsacq_synth_capture", "gpsacq_stage_times", "gpsacq_get_replica_time",
                "gpsacq_get_replica_spectrum", "gpsacq_get_block_spectrum", "gpsacq_get_cell_stats")
 
 
@@ -236,6 +243,25 @@ class Acquisition:
         out = np.zeros(self.n_doppler, CELL_DTYPE)
         self._check(self._lib.gpsacq_get_cell_stats(self._h, block, out.ctypes.data))
         return out
+
+
+def synth_capture_gpu(n_samples: int, fs: float, fc: float, sats, seed: int = 1, noise_sigma: float = 1.0,
+                      nav_bps: float = 50.0, device: int = 0, d_out_ptr: int | None = None) -> np.ndarray | None:
+    """Synthetic packed 1-bit IF capture generated on the GPU (gpsacq_synth_capture).  sats: dicts with prn,
+    amp, doppler_hz, code_phase_chips and optionally carrier_phase_cycles.  Returns the bytes (host) unless
+    d_out_ptr (a device address) is given."""
+    lib = load_library()
+    arr = (_Sat * len(sats))()
+    for i, s in enumerate(sats):
+        arr[i] = _Sat(prn=s["prn"], reserved=0, amp=s["amp"], doppler_hz=s["doppler_hz"],
+                      code_phase_chips=s["code_phase_chips"], carrier_phase_cycles=s.get("carrier_phase_cycles", 0.0))
+    out = None if d_out_ptr else np.zeros((n_samples + 7) // 8, np.uint8)
+    rc = lib.gpsacq_synth_capture(device, fs, fc, arr, len(sats), noise_sigma, nav_bps, seed, n_samples,
+                                  out.ctypes.data if out is not None else None, d_out_ptr)
+    if rc != 0:
+        msg = lib.gpsacq_last_error(None)
+        raise GpsAcqError(f"gpsacq_synth_capture failed ({rc}): {msg.decode() if msg else '?'}")
+    return out
 
 
 class AcquisitionGroup:

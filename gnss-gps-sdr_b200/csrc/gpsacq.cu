@@ -22,6 +22,7 @@
 #include "ga_kernels.cuh"
 #include "ga_grid.cuh"
 #include "ga_frontend.cuh"
+#include "ga_siggen.cuh"
 #include "ga_tables.h"
 
 using namespace ga;
@@ -41,7 +42,8 @@ enum { GID_4000 = 0, GID_8000 = 1, GID_10000 = 2 };
 typedef Geom<2, 20, 20, 10> H4000;     // L = 8000,  W <= 4000
 typedef Geom<2, 20, 20, 20> H8000;     // L = 16000, W <= 8000
 typedef Geom<2, 25, 20, 20> H10000;    // L = 20000, W <= 10000
-enum { HID_4000 = 3, HID_8000 = 4, HID_10000 = 5 };
+typedef Geom<2, 20, 20, 16> H6400;     // L = 12800, W <= 6400 (e.g. 5.456 MHz: 20 % less work than L = 16000)
+enum { HID_4000 = 3, HID_8000 = 4, HID_10000 = 5, HID_6400 = 6 };
 
 #define CELL_T_4000 256
 #ifndef CELL_T_8000
@@ -399,6 +401,7 @@ template <class H, int T, int NW, int HID> struct GridOps {
 
 #define GRID_DISPATCH(h, CALL)                                                                              \
     (h->gid == HID_4000    ? (h->cell_nw == 7 ? GridOps<H4000, 256, 7, HID_4000>::CALL : GridOps<H4000, 256, 10, HID_4000>::CALL)      \
+     : h->gid == HID_6400  ? (h->cell_nw == 14 ? GridOps<H6400, 448, 14, HID_6400>::CALL : GridOps<H6400, 448, 16, HID_6400>::CALL)    \
      : h->gid == HID_8000  ? (h->cell_nw == 14 ? GridOps<H8000, 448, 14, HID_8000>::CALL : GridOps<H8000, 448, 20, HID_8000>::CALL)    \
                            : (h->cell_nw == 17 ? GridOps<H10000, 256, 17, HID_10000>::CALL : GridOps<H10000, 256, 20, HID_10000>::CALL))
 
@@ -419,6 +422,7 @@ static int create_grid(gpsacq *h)
     h->chunk_bytes = h->block_bytes * h->kblocks;
     h->chunk_samples = h->w;
     if (h->w <= H4000::N2) { h->gid = HID_4000; h->n1 = 2; h->n2 = H4000::N2; h->cell_nw = h->w <= 7 * H4000::OUT_STRIDE ? 7 : 10; }
+    else if (h->w <= H6400::N2) { h->gid = HID_6400; h->n1 = 2; h->n2 = H6400::N2; h->cell_nw = h->w <= 14 * H6400::OUT_STRIDE ? 14 : 16; }
     else if (h->w <= H8000::N2) { h->gid = HID_8000; h->n1 = 2; h->n2 = H8000::N2; h->cell_nw = h->w <= 14 * H8000::OUT_STRIDE ? 14 : 20; }
     else if (h->w <= H10000::N2) { h->gid = HID_10000; h->n1 = 2; h->n2 = H10000::N2; h->cell_nw = h->w <= 17 * H10000::OUT_STRIDE ? 17 : 20; }
     else { h->err = "sampling rates above 10 MHz are not supported yet"; return GPSACQ_EINVAL; }
@@ -698,6 +702,36 @@ int gpsacq_iq8_to_bits(gpsacq_t *h, const void *iq, size_t n_samples, int format
     if (rc == GPSACQ_ECUDA) h->err = std::string("front-end: ") + cudaGetErrorString(cudaGetLastError());
     cudaFree(d_iq); cudaFree(d_bits); cudaFree(d_sums);
     return rc;
+}
+
+int gpsacq_synth_capture(int device, double fs, double fc, const gpsacq_sat *sats, int n_sats, double noise_sigma,
+                         double nav_bps, uint64_t seed, size_t n_samples, uint8_t *bits_out, void *d_bits_out)
+{
+    if (!(fs > 0) || n_sats < 0 || n_sats > SYNTH_MAX_SATS || (n_sats && !sats) || (!bits_out && !d_bits_out)) {
+        g_create_error = "gpsacq_synth_capture: bad arguments (at most 16 satellites)"; return GPSACQ_EINVAL;
+    }
+    SynthParams p;
+    memset(&p, 0, sizeof p);
+    p.n_sats = n_sats; p.fs = fs; p.fc = fc; p.sigma = noise_sigma; p.nav_bps = nav_bps > 0 ? nav_bps : 50.0; p.seed = seed;
+    for (int i = 0; i < n_sats; i++) {
+        if (sats[i].prn < 1 || sats[i].prn > 32) { g_create_error = "gpsacq_synth_capture: prn out of range 1..32"; return GPSACQ_EINVAL; }
+        p.sat[i].prn = sats[i].prn; p.sat[i].t0 = kTaps[sats[i].prn - 1][0]; p.sat[i].t1 = kTaps[sats[i].prn - 1][1];
+        p.sat[i].amp = sats[i].amp; p.sat[i].doppler_hz = sats[i].doppler_hz;
+        p.sat[i].code_phase_chips = sats[i].code_phase_chips; p.sat[i].carrier_phase_cycles = sats[i].carrier_phase_cycles;
+    }
+    if (n_samples == 0) return GPSACQ_OK;
+    if (device >= 0 && cudaSetDevice(device) != cudaSuccess) { g_create_error = "gpsacq_synth_capture: cudaSetDevice failed (no CPU fallback)"; return GPSACQ_ECUDA; }
+    const size_t nbytes = (n_samples + 7) / 8;
+    unsigned char *d = (unsigned char *)d_bits_out;
+    bool own = false;
+    if (!d) { if (cudaMalloc(&d, nbytes) != cudaSuccess) { g_create_error = "gpsacq_synth_capture: cudaMalloc failed"; return GPSACQ_ECUDA; } own = true; }
+    synth_bits_kernel<<<(unsigned)((nbytes + 255) / 256), 256>>>(p, n_samples, 0, d);
+    cudaError_t e = cudaGetLastError();
+    if (e == cudaSuccess && bits_out) e = cudaMemcpy(bits_out, d, nbytes, cudaMemcpyDeviceToHost);
+    if (e == cudaSuccess) e = cudaDeviceSynchronize();
+    if (own) cudaFree(d);
+    if (e != cudaSuccess) { g_create_error = std::string("gpsacq_synth_capture: ") + cudaGetErrorString(e); return GPSACQ_ECUDA; }
+    return GPSACQ_OK;
 }
 
 int gpsacq_stage_times(gpsacq_t *h, float ms[4])

@@ -99,3 +99,40 @@ def synth_iq8(n_samples: int, fs: float, sats, seed: int = 7, noise_sigma: float
     iq[0::2], iq[1::2] = np.round(y.real), np.round(y.imag)
     iq = np.clip(iq, -127, 127)
     return iq.astype(np.int8).view(np.uint8) if signed else (iq + 128).astype(np.uint8)
+
+
+# ---- counter-based restatement of the GPU generator (csrc/ga_siggen.cuh), for parity tests -----------------
+_M64 = np.uint64(0xFFFFFFFFFFFFFFFF)
+
+
+def _splitmix64(x: np.ndarray) -> np.ndarray:
+    with np.errstate(over="ignore"):
+        x = (x + np.uint64(0x9E3779B97F4A7C15)) & _M64
+        x = ((x ^ (x >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)) & _M64
+        x = ((x ^ (x >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)) & _M64
+        return x ^ (x >> np.uint64(31))
+
+
+def synth_capture_counter(n_samples: int, fs: float, fc: float, sats, seed: int = 1, noise_sigma: float = 1.0,
+                          nav_bps: float = 50.0) -> np.ndarray:
+    """Same formulas, same splitmix64 counters as synth_bits_kernel: bit-identical except where |x| ~ 1e-15."""
+    n = np.arange(n_samples, dtype=np.uint64)
+    t = n.astype(np.float64) / fs
+    seed64 = np.uint64(seed)
+    x = np.zeros(n_samples)
+    if noise_sigma > 0:
+        a = _splitmix64(seed64 ^ _splitmix64(np.uint64(2) * n))
+        b = _splitmix64(seed64 ^ _splitmix64(np.uint64(2) * n + np.uint64(1)))
+        u1 = ((a >> np.uint64(11)).astype(np.float64) + 1.0) * (1.0 / 9007199254740993.0)
+        u2 = (b >> np.uint64(11)).astype(np.float64) * (1.0 / 9007199254740992.0)
+        x += noise_sigma * np.sqrt(-2.0 * np.log(u1)) * np.cos(2.0 * np.pi * u2)
+    for k, s in enumerate(sats):
+        code = 1.0 - 2.0 * cacode(s["prn"]).astype(np.float64)
+        chip = np.fmod(t * (CPS * (1.0 + s["doppler_hz"] / 1575.42e6)) + s["code_phase_chips"], 1023.0).astype(np.int64)
+        nb = (t * nav_bps).astype(np.uint64)
+        with np.errstate(over="ignore"):
+            key = (np.uint64(0xA5A5000000000000) + (np.uint64(k) << np.uint64(40)) + nb) & _M64
+        nav = np.where(_splitmix64(seed64 ^ _splitmix64(key)) & np.uint64(1), -1.0, 1.0)
+        cyc = (fc + s["doppler_hz"]) * t + s.get("carrier_phase_cycles", 0.0)
+        x += s["amp"] * nav * code[chip] * np.cos(2.0 * np.pi * (cyc - np.floor(cyc)))
+    return pack_bits_lsb_first((x < 0).astype(np.uint8))

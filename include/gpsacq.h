@@ -188,6 +188,21 @@ const char *gpsacq_group_gather_kind(const gpsacq_group_t *g);   /* "nccl" or "h
 const char *gpsacq_group_last_error(const gpsacq_group_t *g);
 gpsacq_t *gpsacq_group_engine(gpsacq_group_t *g, int i);         /* engine of the i-th device (for info/probes) */
 
+/* Synthetic 1-bit IF capture on the GPU (what gps_sig_gen.m + cacode.m produce, generalised: several
+ * satellites, Doppler, code phase, noise).  n_samples real IF samples at fs around IF fc -> packed bits,
+ * LSB first, into bits_out (host, ceil(n/8) bytes) and/or d_bits_out (device); either may be NULL.
+ * Counter-based randomness: the same (seed, sample index) always gives the same noise / NAV bit. */
+typedef struct gpsacq_sat {
+    int32_t prn;                 /* 1..32 */
+    int32_t reserved;
+    double  amp;                 /* carrier amplitude relative to noise_sigma = 1 */
+    double  doppler_hz;
+    double  code_phase_chips;    /* 0..1023 at sample 0 */
+    double  carrier_phase_cycles;
+} gpsacq_sat;
+int  gpsacq_synth_capture(int device, double fs, double fc, const gpsacq_sat *sats, int n_sats, double noise_sigma,
+                          double nav_bps, uint64_t seed, size_t n_samples, uint8_t *bits_out, void *d_bits_out);
+
 /* Elapsed milliseconds of the stages of the most recent batch, measured with CUDA
  * events on the launching stream: [0] unpack+mix+forward FFT kernel, [1] cell kernel
  * (conj-multiply + backward FFT + peak), [2] best-over-Doppler kernel, [3] whole batch.

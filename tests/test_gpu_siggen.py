@@ -1,0 +1,38 @@
+"""GPU synthetic-capture generator vs its numpy restatement, then through the engine."""
+import importlib
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def test_gpu_generator_matches_numpy_restatement_and_is_searchable(ga):
+    sg = importlib.import_module("gnss_gps_sdr_b200.siggen")
+    fs, fc = 5.456e6, 4.092e6
+    sats = sg.default_constellation(fs, cn0_dbhz=47.0, seed=3)
+    for i, s in enumerate(sats):
+        s["carrier_phase_cycles"] = 0.1 * i
+    n = 40960 * 32
+    gpu = ga.synth_capture_gpu(n, fs, fc, sats, seed=77, noise_sigma=1.0)
+    ref = sg.synth_capture_counter(n, fs, fc, sats, seed=77, noise_sigma=1.0)
+    assert gpu.size == ref.size == n // 8
+    flips = int(np.unpackbits(gpu ^ ref).sum())
+    assert flips <= n * 1e-5, f"{flips} of {n} bits differ"          # libm vs CUDA last-ulp differences on near-zero samples
+    # noise-free: the deterministic part alone
+    g0 = ga.synth_capture_gpu(n // 8, fs, fc, sats[:3], seed=5, noise_sigma=0.0)
+    r0 = sg.synth_capture_counter(n // 8, fs, fc, sats[:3], seed=5, noise_sigma=0.0)
+    assert int(np.unpackbits(g0 ^ r0).sum()) <= 4
+    # statistics of the noise: about half the bits set, and the capture is searchable
+    assert abs(np.unpackbits(gpu).mean() - 0.5) < 0.01
+    with ga.Acquisition(fc, fs) as acq:
+        pk = acq.search_blocks(gpu)
+    for s in sats:
+        p = pk[s["prn"] - 1]
+        assert p["snr"] >= 25 and abs(p["lo_shift"] - s["doppler_hz"] * 40000 / fs) <= 1.0
+
+
+def test_gpu_generator_argument_checks(ga):
+    with pytest.raises(ga.GpsAcqError):
+        ga.synth_capture_gpu(64, 5.456e6, 4.092e6, [dict(prn=40, amp=1.0, doppler_hz=0.0, code_phase_chips=0.0)])
+    assert ga.synth_capture_gpu(0, 5.456e6, 4.092e6, []).size == 0
