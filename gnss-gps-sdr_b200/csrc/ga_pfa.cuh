@@ -1,0 +1,190 @@
+// ga_pfa.cuh -- GRID mode kernels on the native W-point prime-factor transforms of ga_pfa.h
+// (W = 5456, 8184, 2800: the 1 ms block lengths of BASELINE.json configs[1..4]).  Same semantics as
+// ga_grid.cuh (the reference's Correlate(), c/search_offline.cpp:169-201, is the
+// template for the conj side and the |.|^2 / first-max / sum statistics) but no zero-padded embedding:
+// a cell reads exactly the 2*W*8 algorithmic bytes and does one W-point backward transform per block.
+#pragma once
+#include "ga_grid.cuh"
+#include "ga_pfa.h"
+
+namespace ga {
+
+// time sample n of (block, Doppler bin d), 32-bit index arithmetic (|d|*W < 2^31 is checked at create)
+struct GridSrc32 {
+    const unsigned char *chunk, *lo;
+    const cf *wipe;
+    int d, m;
+    __device__ __forceinline__ cf operator()(int n) const
+    {
+        const int bit = (chunk[n >> 3] >> (n & 7)) & 1, l = lo[n];
+        const float xr = (bit ^ (l & 1)) ? -1.0f : 1.0f, xi = (bit ^ (l >> 1)) ? -1.0f : 1.0f;
+        int k = (d * n) % m;
+        if (k < 0) k += m;
+        const cf ph = wipe[k];
+        return mk(__fadd_rn(xr * ph.x, -(xi * ph.y)), __fadd_rn(xr * ph.y, xi * ph.x));      // as GridSrc
+    }
+};
+
+// forward transform of every (block, Doppler bin) [MODE 0: conj(X)] or of the 32 one-period replicas
+// [MODE 1: C]; one CTA per item, output in the cell's (a,b,c)-linear order.  F = G::Fwd.
+template <class G, int T, int MODE>
+__global__ void __launch_bounds__(T) pfa_fwd_kernel(const unsigned char *__restrict__ bits, int block_bytes,
+                                                    const unsigned char *__restrict__ lo, const cf *__restrict__ wipe,
+                                                    int n_dop, int dmax, int m, const float *__restrict__ code_w,
+                                                    cf *__restrict__ out)
+{
+    typedef typename G::Fwd F;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    cf *sm = reinterpret_cast<cf *>(smem_raw);
+    const int item = blockIdx.x;
+    if (MODE == 0) {
+        const int blk = item / n_dop, di = item - blk * n_dop;
+        GridSrc32 src{bits + (size_t)blk * block_bytes, lo, wipe, di - dmax, m};
+        for (int j = threadIdx.x; j < F::NA; j += T) pfa_fwd_passA<F>(j, src, sm);
+    } else {
+        RealSrc src{code_w + (size_t)item * G::W};
+        for (int j = threadIdx.x; j < F::NA; j += T) pfa_fwd_passA<F>(j, src, sm);
+    }
+    __syncthreads();
+    for (int j = threadIdx.x; j < F::NB; j += T) pfa_passB<F, -1>(j, sm);
+    __syncthreads();
+    cf *dst = out + (size_t)item * G::W;
+    for (int j = threadIdx.x; j < F::NC; j += T) pfa_fwd_passC_store<F, MODE == 0>(j, sm, dst);
+}
+
+// The native GRID cell kernel.  cell = (acquisition, Doppler bin, PRN), PRN fastest (the 32 cells that
+// share a block spectrum run together).  Per 1 ms block: pass A (coalesced loads of conj(X) and C,
+// multiply, radix-RA) -> smem, pass B in place, pass C -> |y|^2.  K = 1: statistics straight from the
+// registers.  K > 1 (MULTI): the power of each lag is summed over the K blocks in tensor memory
+// (tcgen05.ld/st, as in cell_kernel_tm) and the statistics are taken on the sum.
+template <class G, int T, int MINB, bool MULTI>
+__global__ void __launch_bounds__(T, MINB) pfa_cell_kernel(const cf *__restrict__ xg, const cf *__restrict__ crep,
+                                                           int n_cells, int n_dop, int kblocks, CellStat *__restrict__ cells)
+{
+    static_assert(T % 32 == 0, "whole warps only");
+    constexpr int NWARP = T / 32;
+    constexpr int NTA = cdiv(G::NA, 32), NTB = cdiv(G::NB, 32), NTC = cdiv(G::NC, 32);
+    constexpr int ITA = cdiv(NTA, NWARP), ITB = cdiv(NTB, NWARP), ITC = cdiv(NTC, NWARP);
+    constexpr int NWP = (G::RC + 1) & ~1;                            // power accumulators per butterfly, even
+    constexpr uint32_t COL_SLOT = (uint32_t)((ITC * NWP + 7) & ~7);
+    constexpr uint32_t TM_COLS = pow2_at_least(COL_SLOT * cdiv(NWARP, 4));
+    static_assert(!MULTI || TM_COLS * MINB <= 512, "TMEM columns");
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    cf *sm = reinterpret_cast<cf *>(smem_raw);
+    __shared__ float red_best[NWARP], red_sum[NWARP];
+    __shared__ int red_idx[NWARP];
+    __shared__ uint32_t tm_base_s;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+
+    uint32_t tm_base = 0, tm_mine = 0;
+    if (MULTI) {
+        if (wid == 0) {
+            asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tm_base_s)), "r"(TM_COLS) : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        }
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncthreads();
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        tm_base = tm_base_s;
+        tm_mine = tm_base + ((32u * (uint32_t)(wid & 3)) << 16) + (uint32_t)(wid >> 2) * COL_SLOT;
+    }
+
+    for (int cell = blockIdx.x; cell < n_cells; cell += gridDim.x) {
+        const int acq = cell / (n_dop * 32), r = cell - acq * (n_dop * 32);
+        const int di = r >> 5, prn = r & 31;
+        const cf *cs = crep + (size_t)prn * G::W;
+        float best = 0.0f, sum = 0.0f;
+        int besti = 0;
+
+        for (int k = 0; k < kblocks; k++) {
+            const cf *xs = xg + ((size_t)(acq * kblocks + k) * n_dop + di) * G::W;
+#pragma unroll 1
+            for (int it = 0; it < ITA; it++) {
+                const int j = (wid + it * NWARP) * 32 + lane;
+                if (j < G::NA) pfa_cell_passA<G>(j, xs, cs, sm);
+            }
+            __syncthreads();
+#pragma unroll 1
+            for (int it = 0; it < ITB; it++) {
+                const int j = (wid + it * NWARP) * 32 + lane;
+                if (j < G::NB) pfa_passB<G, +1>(j, sm);
+            }
+            __syncthreads();
+#pragma unroll 1
+            for (int it = 0; it < ITC; it++) {
+                const int task = wid + it * NWARP;
+                if (task < NTC) {                                   // warp-uniform
+                    const int j = task * 32 + lane;
+                    const bool act = j < G::NC;
+                    const int jc = act ? j : G::NC - 1;             // idle lanes shadow the last butterfly (TMEM ops are warp-wide)
+                    const int t0 = pfa_passC_t0<G>(jc);
+                    if (!MULTI) {
+                        // K = 1: power and statistics straight from the butterfly's output stream
+                        PfaPeak<G> pk;
+                        pk.init(t0);
+                        pfa_passC<G, +1>(jc, sm, [&](auto wc, cf v) { pk.template put<decltype(wc)::value>(fmaf(v.x, v.x, v.y * v.y)); });
+                        if (act) pk.merge(best, besti, sum);
+                    } else {
+                        float pw[NWP];
+                        if (NWP > G::RC) pw[NWP - 1] = 0.0f;
+                        pfa_passC<G, +1>(jc, sm, [&](auto wc, cf v) { pw[decltype(wc)::value] = fmaf(v.x, v.x, v.y * v.y); });
+                        const uint32_t pcol = tm_mine + (uint32_t)(it * NWP);
+                        if (k > 0) {
+                            float old[NWP];
+                            tm_move<NWP, true>(pcol, old);
+                            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+                            for (int w = 0; w < G::RC; w++) pw[w] = old[w] + pw[w];       // blocks in ascending order (App. E)
+                        }
+                        if (k < kblocks - 1) {
+                            tm_move<NWP, false>(pcol, pw);
+                        } else if (act) {
+                            PfaPeak<G> pk;
+                            pk.init(t0);
+                            static_for<0, G::RC>([&](auto wc) { pk.template put<decltype(wc)::value>(pw[decltype(wc)::value]); });
+                            pk.merge(best, besti, sum);
+                        }
+                    }
+                }
+            }
+            if (MULTI) asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+            __syncthreads();                                        // smem is rewritten by the next pass A
+        }
+
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) {
+            const float ob = __shfl_down_sync(0xffffffffu, best, off);
+            const int oi = __shfl_down_sync(0xffffffffu, besti, off);
+            const float os = __shfl_down_sync(0xffffffffu, sum, off);
+            if (ob > best || (ob == best && oi < besti)) { best = ob; besti = oi; }
+            sum += os;
+        }
+        if (lane == 0) { red_best[wid] = best; red_idx[wid] = besti; red_sum[wid] = sum; }
+        __syncthreads();
+        if (wid == 0) {
+            best = lane < NWARP ? red_best[lane] : 0.0f;
+            besti = lane < NWARP ? red_idx[lane] : 0x7fffffff;
+            sum = lane < NWARP ? red_sum[lane] : 0.0f;
+#pragma unroll
+            for (int off = 16; off > 0; off >>= 1) {
+                const float ob = __shfl_down_sync(0xffffffffu, best, off);
+                const int oi = __shfl_down_sync(0xffffffffu, besti, off);
+                const float os = __shfl_down_sync(0xffffffffu, sum, off);
+                if (ob > best || (ob == best && oi < besti)) { best = ob; besti = oi; }
+                sum += os;
+            }
+            if (lane == 0) {
+                CellStat rec; rec.max_pwr = best; rec.tot_pwr = sum; rec.max_idx = besti; rec.pad = 0;
+                cells[((size_t)acq * 32 + prn) * n_dop + di] = rec;
+            }
+        }
+        // red_* are rewritten only after the next cell's barriers
+    }
+    if (MULTI) {
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncthreads();
+        if (wid == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tm_base), "r"(TM_COLS) : "memory");
+    }
+}
+
+}  // namespace ga

@@ -37,6 +37,13 @@ constexpr int cx_inv_mod(int a, int m)
     return 1;
 }
 
+// compile-time loop: the body receives std::integral_constant<int, I>, so that
+// twiddles can be formed as constexpr immediates
+template <int I, int NITER, class F> GA_HD void static_for(F &&f)
+{
+    if constexpr (I < NITER) { f(std::integral_constant<int, I>{}); static_for<I + 1, NITER>(f); }
+}
+
 // ---- primitives --------------------------------------------------------------
 template <int R, int DIR> struct Radix;
 
@@ -116,12 +123,6 @@ template <int R1, int R2, int DIR> struct PFA {
 };
 
 // ---- Cooley-Tukey: R = R1*R2 with compile-time twiddles -----------------------
-// compile-time loop: the body receives std::integral_constant<int, I>, so that
-// twiddles can be formed as constexpr immediates
-template <int I, int NITER, class F> GA_HD void static_for(F &&f)
-{
-    if constexpr (I < NITER) { f(std::integral_constant<int, I>{}); static_for<I + 1, NITER>(f); }
-}
 
 template <int R1, int R2, int DIR> struct CT {
     static constexpr int R = R1 * R2;
@@ -156,11 +157,78 @@ template <int R1, int R2, int DIR> struct CT {
     }
 };
 
+// ---- odd prime radix: direct evaluation with the conjugate-pair symmetry -------
+// X_j = x0 + sum_{k=1..H} [ cos(2 pi jk/P) (x_k + x_{P-k}) + DIR*i*sin(2 pi jk/P) (x_k - x_{P-k}) ],  H = (P-1)/2,
+// X_{P-j} = the same with the sign of the sine part flipped.  All cosines / sines are compile-time
+// immediates (on sm_100a FFMA2 takes a broadcast 32-bit immediate, so a term costs one instruction
+// per pair and no register); 2*H*H + O(P) packed operations per butterfly.  Used for the radices the
+// 1 ms GPS block lengths need: 5456 = 16*11*31, 8184 = 24*11*31, 2800 = 16*25*7.
+template <int P, int DIR> struct RadixPrime {
+    static constexpr int H = (P - 1) / 2;
+    // streaming form: emit(std::integral_constant<int, j>, X_j) is called as soon as an output is complete
+    // (order 0, 1, P-1, 2, P-2, ...), so a consumer that reduces or stores the outputs never holds all P
+    // of them next to the 2*H sums and differences.
+    template <class Emit> static GA_HD void run_emit(const cf (&x)[P], Emit &&emit)
+    {
+        cf s[H], d[H];
+        GA_UNROLL
+        for (int k = 1; k <= H; k++) { s[k - 1] = cadd(x[k], x[P - k]); d[k - 1] = csub(x[k], x[P - k]); }
+        const cf x0 = x[0];
+        {   // X_0: pairwise tree
+            cf t[H];
+            GA_UNROLL
+            for (int k = 0; k < H; k++) t[k] = s[k];
+            GA_UNROLL
+            for (int n = H; n > 1; n = (n + 1) / 2) {
+                GA_UNROLL
+                for (int k = 0; k < n / 2; k++) t[k] = cadd(t[k], t[n - 1 - k]);
+            }
+            emit(std::integral_constant<int, 0>{}, cadd(x0, t[0]));
+        }
+        static_for<1, H + 1>([&](auto jc) {
+            constexpr int j = decltype(jc)::value;
+            cf a = x0, b = mk(0.0f, 0.0f);
+            static_for<1, H + 1>([&](auto kc) {
+                constexpr int k = decltype(kc)::value;
+                constexpr float c = (float)cx_cos2pi(j * k, P), sn = (float)cx_sin2pi(j * k, P);
+                a = caxpy(a, s[k - 1], c);
+                b = (k == 1) ? cscale(d[0], sn) : caxpy(b, d[k - 1], sn);
+            });
+            emit(std::integral_constant<int, j>{}, cadd_i<DIR>(a, b));          // a + DIR*i*b
+            emit(std::integral_constant<int, P - j>{}, csub_i<DIR>(a, b));
+        });
+    }
+    static GA_HD void run(cf (&x)[P])
+    {
+        cf y[P];
+        run_emit(x, [&](auto ic, cf v) { y[decltype(ic)::value] = v; });
+        GA_UNROLL
+        for (int k = 0; k < P; k++) x[k] = y[k];
+    }
+};
+template <int DIR> struct Radix<3, DIR>  { static GA_HD void run(cf (&x)[3])  { RadixPrime<3, DIR>::run(x); } };
+template <int DIR> struct Radix<7, DIR>  { static GA_HD void run(cf (&x)[7])  { RadixPrime<7, DIR>::run(x); } };
+template <int DIR> struct Radix<11, DIR> { static GA_HD void run(cf (&x)[11]) { RadixPrime<11, DIR>::run(x); } };
+template <int DIR> struct Radix<31, DIR> { static GA_HD void run(cf (&x)[31]) { RadixPrime<31, DIR>::run(x); } };
+
 template <int DIR> struct Radix<8, DIR>  { static GA_HD void run(cf (&x)[8])  { CT<2, 4, DIR>::run(x); } };
 template <int DIR> struct Radix<10, DIR> { static GA_HD void run(cf (&x)[10]) { PFA<2, 5, DIR>::run(x); } };
 template <int DIR> struct Radix<16, DIR> { static GA_HD void run(cf (&x)[16]) { CT<4, 4, DIR>::run(x); } };
 template <int DIR> struct Radix<20, DIR> { static GA_HD void run(cf (&x)[20]) { PFA<4, 5, DIR>::run(x); } };
 template <int DIR> struct Radix<25, DIR> { static GA_HD void run(cf (&x)[25]) { CT<5, 5, DIR>::run(x); } };
+template <int DIR> struct Radix<24, DIR> { static GA_HD void run(cf (&x)[24]) { PFA<3, 8, DIR>::run(x); } };
+
+// radix-R butterfly with streamed outputs: emit(std::integral_constant<int, k>, X_k).  Prime radices
+// stream for real (see RadixPrime); the others run in place and then emit in index order.
+constexpr bool cx_streams(int r) { return r == 3 || r == 7 || r == 11 || r == 31; }
+template <int R, int DIR, class Emit> GA_HD void radix_emit(cf (&p)[R], Emit &&emit)
+{
+    if constexpr (cx_streams(R)) RadixPrime<R, DIR>::run_emit(p, emit);
+    else {
+        Radix<R, DIR>::run(p);
+        static_for<0, R>([&](auto ic) { emit(ic, p[decltype(ic)::value]); });
+    }
+}
 
 // powers of a unit complex number: w[k] = base^k, k < R, by a balanced product
 // tree (depth ~log2 R, so rounding stays at a few ulp).  w[0] is 1.

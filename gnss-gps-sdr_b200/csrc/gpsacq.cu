@@ -21,6 +21,7 @@
 #define TM_MINB CELL_MINB
 #include "ga_kernels.cuh"
 #include "ga_grid.cuh"
+#include "ga_pfa.cuh"
 #include "ga_frontend.cuh"
 #include "ga_siggen.cuh"
 #include "ga_tables.h"
@@ -44,6 +45,30 @@ typedef Geom<2, 20, 20, 20> H8000;     // L = 16000, W <= 8000
 typedef Geom<2, 25, 20, 20> H10000;    // L = 20000, W <= 10000
 typedef Geom<2, 20, 20, 16> H6400;     // L = 12800, W <= 6400 (e.g. 5.456 MHz: 20 % less work than L = 16000)
 enum { HID_4000 = 3, HID_8000 = 4, HID_10000 = 5, HID_6400 = 6 };
+// GRID mode, native W-point prime-factor transforms (ga_pfa.h) for the 1 ms block lengths of the named
+// sampling rates; any other W goes through the embedding above.
+typedef PGeom<16, 11, 31> P5456;       // fs = 5.456 MHz
+typedef PGeom<24, 11, 31> P8184;       // fs = 8.184 MHz
+typedef PGeom<16, 25, 7> P2800;        // fs = 2.8 MHz
+enum { PID_5456 = 7, PID_8184 = 8, PID_2800 = 9 };
+#ifndef PFA_T_5456
+#define PFA_T_5456 128      // 4 warps (a multiple of the 4 sub-partitions keeps the per-thread register budget whole)
+#endif
+#ifndef PFA_B_5456
+#define PFA_B_5456 4
+#endif
+#ifndef PFA_T_8184
+#define PFA_T_8184 256
+#endif
+#ifndef PFA_B_8184
+#define PFA_B_8184 2
+#endif
+#ifndef PFA_T_2800
+#define PFA_T_2800 128
+#endif
+#ifndef PFA_B_2800
+#define PFA_B_2800 4
+#endif
 
 #define CELL_T_4000 256
 #ifndef CELL_T_8000
@@ -399,11 +424,75 @@ template <class H, int T, int NW, int HID> struct GridOps {
     static int consts(gpsacq *h) { return upload_const_t<H, HID>(h); }
 };
 
+template <class G, int T, int MINB, bool MULTI> struct PfaOps {
+    static int setup(gpsacq *h)
+    {
+        auto kern = pfa_cell_kernel<G, T, MINB, MULTI>;
+        h->cell_smem = (int)(G::SMEM_ELEMS * sizeof(cf));
+        h->cell_threads = T; h->cell_nw = G::RC;
+        CUDA_TRY(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, h->cell_smem));
+        const int want = MINB * (h->cell_smem + 2048);
+        int pct = (int)((want * 100LL + 228 * 1024 - 1) / (228 * 1024));
+        if (pct > 100) pct = 100;
+        CUDA_TRY(h, cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, pct));
+        int per_sm = 0;
+        CUDA_TRY(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, T, h->cell_smem));
+        if (per_sm < 1) { h->err = "GRID cell kernel does not fit on an SM"; return GPSACQ_ECUDA; }
+        if (MULTI && per_sm < MINB) per_sm = MINB;      // TMEM kernels: the occupancy query is conservative (setup_cells_t)
+        h->cell_ctas = per_sm * h->sm_count;
+        typedef typename G::Fwd F;
+        const int fsm = (int)(F::SMEM_ELEMS * sizeof(cf));
+        CUDA_TRY(h, cudaFuncSetAttribute(pfa_fwd_kernel<G, FWD_T, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, fsm));
+        CUDA_TRY(h, cudaFuncSetAttribute(pfa_fwd_kernel<G, FWD_T, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, fsm));
+        return 0;
+    }
+    static int fwd_blocks(gpsacq *h, size_t n_blocks, const unsigned char *d_bits)
+    {
+        typedef typename G::Fwd F;
+        pfa_fwd_kernel<G, FWD_T, 0><<<(unsigned)(n_blocks * h->ndop), FWD_T, F::SMEM_ELEMS * sizeof(cf), h->stream>>>(
+            d_bits, h->block_bytes, h->d_lo, h->d_wipe, h->ndop, h->dmax, h->wipe_m, nullptr, h->d_xg);
+        CUDA_TRY(h, cudaGetLastError());
+        return 0;
+    }
+    static int cells(gpsacq *h, size_t n_acq)
+    {
+        const int n_cells = (int)(n_acq * 32 * (size_t)h->ndop);
+        const int grid = std::min(n_cells, h->cell_ctas);
+        pfa_cell_kernel<G, T, MINB, MULTI><<<grid, T, h->cell_smem, h->stream>>>(h->d_xg, h->d_cext, n_cells, h->ndop, h->kblocks, h->d_cells);
+        CUDA_TRY(h, cudaGetLastError());
+        return 0;
+    }
+    static int replicas(gpsacq *h)
+    {
+        typedef typename G::Fwd F;
+        pfa_fwd_kernel<G, FWD_T, 1><<<32, FWD_T, F::SMEM_ELEMS * sizeof(cf), h->stream>>>(
+            nullptr, 0, nullptr, nullptr, 1, 0, 1, h->d_code_w, h->d_cext);
+        CUDA_TRY(h, cudaGetLastError());
+        return 0;
+    }
+    static int consts(gpsacq *) { return 0; }            // no twiddle tables: Good-Thomas
+};
+
+#define PFA_DISPATCH(h, CALL)                                                                               \
+    (h->gid == PID_5456   ? (h->kblocks > 1 ? PfaOps<P5456, PFA_T_5456, PFA_B_5456, true>::CALL : PfaOps<P5456, PFA_T_5456, PFA_B_5456, false>::CALL) \
+     : h->gid == PID_8184 ? (h->kblocks > 1 ? PfaOps<P8184, PFA_T_8184, PFA_B_8184, true>::CALL : PfaOps<P8184, PFA_T_8184, PFA_B_8184, false>::CALL) \
+                          : (h->kblocks > 1 ? PfaOps<P2800, PFA_T_2800, PFA_B_2800, true>::CALL : PfaOps<P2800, PFA_T_2800, PFA_B_2800, false>::CALL))
+
 #define GRID_DISPATCH(h, CALL)                                                                              \
-    (h->gid == HID_4000    ? (h->cell_nw == 7 ? GridOps<H4000, 256, 7, HID_4000>::CALL : GridOps<H4000, 256, 10, HID_4000>::CALL)      \
+    (h->gid >= PID_5456    ? PFA_DISPATCH(h, CALL)                                                          \
+     : h->gid == HID_4000    ? (h->cell_nw == 7 ? GridOps<H4000, 256, 7, HID_4000>::CALL : GridOps<H4000, 256, 10, HID_4000>::CALL)      \
      : h->gid == HID_6400  ? (h->cell_nw == 14 ? GridOps<H6400, 448, 14, HID_6400>::CALL : GridOps<H6400, 448, 16, HID_6400>::CALL)    \
      : h->gid == HID_8000  ? (h->cell_nw == 14 ? GridOps<H8000, 448, 14, HID_8000>::CALL : GridOps<H8000, 448, 20, HID_8000>::CALL)    \
                            : (h->cell_nw == 17 ? GridOps<H10000, 256, 17, HID_10000>::CALL : GridOps<H10000, 256, 20, HID_10000>::CALL))
+
+// native transform available for this block length?  (GPSACQ_GRID_EMBED=1 forces the embedding, for A/B runs)
+static int pfa_gid_for(int w, int dmax)
+{
+    const char *e = getenv("GPSACQ_GRID_EMBED");
+    if (e && *e && *e != '0') return -1;
+    if ((long long)dmax * w >= (1LL << 31)) return -1;          // GridSrc32 index arithmetic
+    return w == P5456::W ? PID_5456 : w == P8184::W ? PID_8184 : w == P2800::W ? PID_2800 : -1;
+}
 
 static int create_grid(gpsacq *h)
 {
@@ -421,7 +510,9 @@ static int create_grid(gpsacq *h)
     h->block_bytes = h->w / 8;
     h->chunk_bytes = h->block_bytes * h->kblocks;
     h->chunk_samples = h->w;
-    if (h->w <= H4000::N2) { h->gid = HID_4000; h->n1 = 2; h->n2 = H4000::N2; h->cell_nw = h->w <= 7 * H4000::OUT_STRIDE ? 7 : 10; }
+    const int pgid = pfa_gid_for(h->w, h->dmax);
+    if (pgid >= 0) { h->gid = pgid; h->n1 = 1; h->n2 = h->w; h->cell_nw = 0; }
+    else if (h->w <= H4000::N2) { h->gid = HID_4000; h->n1 = 2; h->n2 = H4000::N2; h->cell_nw = h->w <= 7 * H4000::OUT_STRIDE ? 7 : 10; }
     else if (h->w <= H6400::N2) { h->gid = HID_6400; h->n1 = 2; h->n2 = H6400::N2; h->cell_nw = h->w <= 14 * H6400::OUT_STRIDE ? 14 : 16; }
     else if (h->w <= H8000::N2) { h->gid = HID_8000; h->n1 = 2; h->n2 = H8000::N2; h->cell_nw = h->w <= 14 * H8000::OUT_STRIDE ? 14 : 20; }
     else if (h->w <= H10000::N2) { h->gid = HID_10000; h->n1 = 2; h->n2 = H10000::N2; h->cell_nw = h->w <= 17 * H10000::OUT_STRIDE ? 17 : 20; }
@@ -493,8 +584,10 @@ static int create_grid(gpsacq *h)
     for (int sv = 0; sv < 32; sv++) { taps.t0[sv] = kTaps[sv][0]; taps.t1[sv] = kTaps[sv][1]; }
     replica_time_kernel<<<32, 256, 0, h->stream>>>(taps, h->d_chip_idx, h->d_blend_a, h->d_blend_b, h->w, h->d_code_w);
     CUDA_TRY(h, cudaGetLastError());
-    grid_replica_extend_kernel<<<dim3(16, 32), 256, 0, h->stream>>>(h->d_code_w, h->w, h->n, (float)((double)h->w / (double)h->n), h->d_repl_time);
-    CUDA_TRY(h, cudaGetLastError());
+    if (h->gid < PID_5456) {       // embedding: two code periods, zero-padded to L (native transforms read d_code_w directly)
+        grid_replica_extend_kernel<<<dim3(16, 32), 256, 0, h->stream>>>(h->d_code_w, h->w, h->n, (float)((double)h->w / (double)h->n), h->d_repl_time);
+        CUDA_TRY(h, cudaGetLastError());
+    }
     rc = GRID_DISPATCH(h, replicas(h));
     if (rc) return rc;
     CUDA_TRY(h, cudaStreamSynchronize(h->stream));

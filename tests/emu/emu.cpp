@@ -10,6 +10,7 @@
 #include <cstring>
 #include "ga_fft3.h"
 #include "ga_tables.h"
+#include "ga_pfa.h"
 
 using namespace ga;
 
@@ -96,6 +97,48 @@ static void emu_fwd_t(const cf *x, int s, cf *out)
     }
 }
 
+// ---- native W-point prime-factor transforms (ga_pfa.h), thread by thread like pfa_fwd_kernel / pfa_cell_kernel
+template <class G>
+static void emu_pfa_fwd_t(const cf *x, int conj, cf *out)
+{
+    typedef typename G::Fwd F;
+    std::vector<cf> sm((size_t)F::SMEM_ELEMS);
+    TimeSrc src{x};
+    for (int j = 0; j < F::NA; j++) pfa_fwd_passA<F>(j, src, sm.data());
+    for (int j = 0; j < F::NB; j++) pfa_passB<F, -1>(j, sm.data());
+    for (int j = 0; j < F::NC; j++) {
+        if (conj) pfa_fwd_passC_store<F, true>(j, sm.data(), out);
+        else pfa_fwd_passC_store<F, false>(j, sm.data(), out);
+    }
+}
+
+template <class G>
+static void emu_pfa_cell_t(const cf *xs, const cf *cs, cf *y, float *best, int *besti, float *sum)
+{
+    std::vector<cf> sm((size_t)G::SMEM_ELEMS);
+    for (int j = 0; j < G::NA; j++) pfa_cell_passA<G>(j, xs, cs, sm.data());
+    for (int j = 0; j < G::NB; j++) pfa_passB<G, +1>(j, sm.data());
+    float b = 0, s_ = 0; int bi = 0;
+    for (int j = 0; j < G::NC; j++) {
+        cf p[G::RC];
+        const int t0 = pfa_passC_t0<G>(j);
+        PfaPeak<G> pk;
+        pk.init(t0);
+        pfa_passC<G, +1>(j, sm.data(), [&](auto wc, cf v) {
+            constexpr int w = decltype(wc)::value;
+            p[w] = v;
+            pk.template put<w>(fmaf(v.x, v.x, v.y * v.y));
+        });
+        for (int w = 0; w < G::RC; w++) y[pfa_lag<G>(t0, w)] = p[w];
+        pk.merge(b, bi, s_);
+    }
+    *best = b; *besti = bi; *sum = s_;
+}
+
+typedef PGeom<16, 11, 31> P5456;
+typedef PGeom<24, 11, 31> P8184;
+typedef PGeom<16, 25, 7> P2800;
+
 typedef Geom<5, 20, 20, 20, true> G8000;
 typedef Geom<4, 25, 20, 20> G10000;
 typedef Geom<10, 20, 20, 10> G4000;
@@ -119,6 +162,46 @@ int emu_cell(int id, const float *xd_blk, const float *cext_sv, int dop, int wle
     case 0: emu_cell_t<G8000>((const cf *)xd_blk, (const cf *)cext_sv, dop, wlen, (cf *)y, best, besti, sum); return 0;
     case 1: emu_cell_t<G10000>((const cf *)xd_blk, (const cf *)cext_sv, dop, wlen, (cf *)y, best, besti, sum); return 0;
     case 2: emu_cell_t<G4000>((const cf *)xd_blk, (const cf *)cext_sv, dop, wlen, (cf *)y, best, besti, sum); return 0;
+    }
+    return -1;
+}
+
+// x: W complex time samples; out: W spectral values in the cell's (a,b,c)-linear order (conjugated if conj)
+int emu_pfa_fwd(int w, const float *x, int conj, float *out)
+{
+    switch (w) {
+    case 5456: emu_pfa_fwd_t<P5456>((const cf *)x, conj, (cf *)out); return 0;
+    case 8184: emu_pfa_fwd_t<P8184>((const cf *)x, conj, (cf *)out); return 0;
+    case 2800: emu_pfa_fwd_t<P2800>((const cf *)x, conj, (cf *)out); return 0;
+    }
+    return -1;
+}
+
+// (a,b,c)-linear position m -> spectral index k (Good's map), for the tests
+int emu_pfa_order(int w, int *k_of_m)
+{
+    auto fill = [&](auto g) {
+        typedef decltype(g) G;
+        for (int a = 0; a < G::RA; a++)
+            for (int b = 0; b < G::RB; b++)
+                for (int c = 0; c < G::RC; c++)
+                    k_of_m[(a * G::RB + b) * G::RC + c] = (int)(((long long)a * G::KA + (long long)b * G::KB + (long long)c * G::KC) % G::W);
+    };
+    switch (w) {
+    case 5456: fill(P5456{}); return 0;
+    case 8184: fill(P8184{}); return 0;
+    case 2800: fill(P2800{}); return 0;
+    }
+    return -1;
+}
+
+// xs = conj(X), cs = C, both in (a,b,c)-linear order; y: W outputs in natural lag order
+int emu_pfa_cell(int w, const float *xs, const float *cs, float *y, float *best, int *besti, float *sum)
+{
+    switch (w) {
+    case 5456: emu_pfa_cell_t<P5456>((const cf *)xs, (const cf *)cs, (cf *)y, best, besti, sum); return 0;
+    case 8184: emu_pfa_cell_t<P8184>((const cf *)xs, (const cf *)cs, (cf *)y, best, besti, sum); return 0;
+    case 2800: emu_pfa_cell_t<P2800>((const cf *)xs, (const cf *)cs, (cf *)y, best, besti, sum); return 0;
     }
     return -1;
 }

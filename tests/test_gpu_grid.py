@@ -22,6 +22,7 @@ CASES = [
     (8.184e6, 2.046e6, 5000.0, 500.0, 1, 2, 50.0),      # configs[2]
     (2.8e6, 0.62e6, 10000.0, 250.0, 4, 2, 47.0),        # configs[3] shape (K>1, 250 Hz), reduced span for the CPU oracle
     (8.184e6, 2.046e6, 3000.0, 100.0, 3, 1, 47.0),      # configs[4] shape (100 Hz step, K>1), reduced span
+    (4.0e6, 1.0e6, 5000.0, 500.0, 2, 2, 50.0),          # W = 4000: no native transform -> zero-padded embedding path
 ]
 
 
@@ -57,6 +58,37 @@ def test_grid_vs_oracle(ga, oracle_mod, siggen, fs, fc, max_fo, step, K, n_acq, 
                     assert abs(p["lo_shift"] * step - s["doppler_hz"]) <= step
     finally:
         acq.close()
+
+
+@pytest.mark.parametrize("fs,fc,K", [(5.456e6, 4.092e6, 1), (8.184e6, 2.046e6, 2), (2.8e6, 0.62e6, 3)])
+def test_grid_native_transform_matches_embedding(ga, siggen, monkeypatch, fs, fc, K):
+    """The native W-point prime-factor path (csrc/ga_pfa.cuh) and the zero-padded embedding (csrc/ga_grid.cuh)
+    compute the same circular correlations: same integers, powers within float rounding."""
+    W = int(round(fs / 1000))
+    sats = siggen.default_constellation(fs, cn0_dbhz=50.0, seed=5, max_doppler=4000.0)
+    bits = siggen.synth_capture(W * K * 3, fs, fc, sats, seed=12)
+    res = {}
+    for name, env in (("native", None), ("embed", "1")):
+        if env is None:
+            monkeypatch.delenv("GPSACQ_GRID_EMBED", raising=False)
+        else:
+            monkeypatch.setenv("GPSACQ_GRID_EMBED", env)
+        acq = ga.Acquisition(fc, fs, 5000.0, mode=1, doppler_step=500.0, noncoh_blocks=K)
+        try:
+            assert (acq.info["fft_len"] == W) == (name == "native")
+            res[name] = (acq.acquire(bits).copy(), [acq.cell_stats(2 * 32 + p).copy() for p in (0, 7, 31)])
+        finally:
+            acq.close()
+    a, b = res["native"], res["embed"]
+    det = b[0]["snr"] >= 25
+    assert det.sum() >= 3
+    assert np.array_equal(a[0]["lo_shift"][det], b[0]["lo_shift"][det])
+    assert np.array_equal(a[0]["ca_shift"][det], b[0]["ca_shift"][det])
+    assert np.abs(a[0]["snr"][det] / b[0]["snr"][det] - 1).max() <= 5e-5
+    for ca, cb in zip(a[1], b[1]):
+        assert np.abs(ca["max_pwr"] / cb["max_pwr"] - 1).max() <= 5e-5
+        assert np.abs(ca["tot_pwr"] / cb["tot_pwr"] - 1).max() <= 5e-5
+        assert (ca["max_idx"] != cb["max_idx"]).sum() <= 1
 
 
 def test_grid_agrees_with_ref_mode_on_the_capture(ga, engines_ref=None):

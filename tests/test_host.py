@@ -165,3 +165,36 @@ def test_kernel_math_replay_matches_numpy(gid, W):
         pw = np.abs(y[:W]) ** 2
         assert bi.value == int(pw.argmax())
         assert abs(best.value / pw.max() - 1) < 1e-5 and abs(sm.value / pw.sum() - 1) < 1e-5
+
+
+@pytest.mark.parametrize("W", [5456, 8184, 2800])
+def test_pfa_kernel_math_replay_matches_numpy(W):
+    """Native W-point prime-factor transforms (csrc/ga_pfa.h) replayed per thread on the CPU: forward transform
+    into the (a,b,c)-linear order, then product + backward transform + statistics of one GRID cell."""
+    L = _emu()
+    fp = ctypes.POINTER(ctypes.c_float)
+    P = lambda a: a.ctypes.data_as(fp)
+    order = np.zeros(W, np.int32)
+    assert L.emu_pfa_order(W, order.ctypes.data_as(ctypes.POINTER(ctypes.c_int))) == 0
+    assert sorted(order.tolist()) == list(range(W))                # Good's map is a permutation
+    rng = np.random.default_rng(W)
+    x = (rng.standard_normal(W) + 1j * rng.standard_normal(W)).astype(np.complex64)
+    c = (rng.standard_normal(W)).astype(np.complex64)
+    X = np.fft.fft(x.astype(np.complex128))
+    C = np.fft.fft(c.astype(np.complex128))
+    xs = np.zeros(W, np.complex64)
+    cs = np.zeros(W, np.complex64)
+    assert L.emu_pfa_fwd(W, P(x.view(np.float32)), 1, P(xs.view(np.float32))) == 0
+    assert L.emu_pfa_fwd(W, P(c.view(np.float32)), 0, P(cs.view(np.float32))) == 0
+    assert np.abs(xs - np.conj(X)[order]).max() <= 2e-6 * np.abs(X).max()
+    assert np.abs(cs - C[order]).max() <= 2e-6 * np.abs(C).max()
+    inv = np.argsort(order)                                        # natural spectral index -> position
+    y = np.fft.ifft(xs.astype(np.complex128)[inv] * cs.astype(np.complex128)[inv]) * W     # conj(X)*C, backward
+    yy = np.zeros(W, np.complex64)
+    best, bi, sm = ctypes.c_float(), ctypes.c_int(), ctypes.c_float()
+    assert L.emu_pfa_cell(W, P(xs.view(np.float32)), P(cs.view(np.float32)), P(yy.view(np.float32)),
+                          ctypes.byref(best), ctypes.byref(bi), ctypes.byref(sm)) == 0
+    assert np.abs(yy - y).max() <= 3e-6 * np.abs(y).max()
+    pw = np.abs(y) ** 2
+    assert bi.value == int(pw.argmax())
+    assert abs(best.value / pw.max() - 1) < 1e-5 and abs(sm.value / pw.sum() - 1) < 1e-5
