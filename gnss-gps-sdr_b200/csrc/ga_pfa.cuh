@@ -52,6 +52,17 @@ __global__ void __launch_bounds__(T) pfa_fwd_kernel(const unsigned char *__restr
     for (int j = threadIdx.x; j < F::NC; j += T) pfa_fwd_passC_store<F, MODE == 0>(j, sm, dst);
 }
 
+// slow path of the K = 1 statistics: redo one pass-C butterfly (its inputs are still in shared memory)
+// comparing lags on every tie.  Kept out of line: it is practically never executed.
+template <class G>
+__device__ __noinline__ void pfa_passC_exact(int jc, const cf *sm, int t0, float &best, int &besti, float &sum)
+{
+    PfaPeakExact<G> pk;
+    pk.init(t0);
+    pfa_passC<G, +1>(jc, sm, [&](auto wc, cf v) { pk.template put<decltype(wc)::value>(fmaf(v.x, v.x, v.y * v.y)); });
+    pk.merge(best, besti, sum);
+}
+
 // The native GRID cell kernel.  cell = (acquisition, Doppler bin, PRN), PRN fastest (the 32 cells that
 // share a block spectrum run together).  Per 1 ms block: pass A (coalesced loads of conj(X) and C,
 // multiply, radix-RA) -> smem, pass B in place, pass C -> |y|^2.  K = 1: statistics straight from the
@@ -123,7 +134,10 @@ __global__ void __launch_bounds__(T, MINB) pfa_cell_kernel(const cf *__restrict_
                         PfaPeak<G> pk;
                         pk.init(t0);
                         pfa_passC<G, +1>(jc, sm, [&](auto wc, cf v) { pk.template put<decltype(wc)::value>(fmaf(v.x, v.x, v.y * v.y)); });
-                        if (act) pk.merge(best, besti, sum);
+                        if (act) {
+                            if (!pk.tie) pk.merge(best, besti, sum);
+                            else pfa_passC_exact<G>(jc, sm, t0, best, besti, sum);
+                        }
                     } else {
                         float pw[NWP];
                         if (NWP > G::RC) pw[NWP - 1] = 0.0f;
@@ -142,26 +156,36 @@ __global__ void __launch_bounds__(T, MINB) pfa_cell_kernel(const cf *__restrict_
                             PfaPeak<G> pk;
                             pk.init(t0);
                             static_for<0, G::RC>([&](auto wc) { pk.template put<decltype(wc)::value>(pw[decltype(wc)::value]); });
-                            pk.merge(best, besti, sum);
+                            if (!pk.tie) pk.merge(best, besti, sum);
+                            else {
+                                PfaPeakExact<G> pe;
+                                pe.init(t0);
+                                static_for<0, G::RC>([&](auto wc) { pe.template put<decltype(wc)::value>(pw[decltype(wc)::value]); });
+                                pe.merge(best, besti, sum);
+                            }
                         }
                     }
                 }
             }
+            if (k == kblocks - 1) {
+                // the cell is complete: warp-shuffle reduction (ties to the lower lag = first maximum, :192),
+                // per-warp partials to smem BEFORE the barrier that also frees smem for the next pass A
+#pragma unroll
+                for (int off = 16; off > 0; off >>= 1) {
+                    const float ob = __shfl_down_sync(0xffffffffu, best, off);
+                    const int oi = __shfl_down_sync(0xffffffffu, besti, off);
+                    const float os = __shfl_down_sync(0xffffffffu, sum, off);
+                    if (ob > best || (ob == best && oi < besti)) { best = ob; besti = oi; }
+                    sum += os;
+                }
+                if (lane == 0) { red_best[wid] = best; red_idx[wid] = besti; red_sum[wid] = sum; }
+            }
             if (MULTI) asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
             __syncthreads();                                        // smem is rewritten by the next pass A
         }
-
-#pragma unroll
-        for (int off = 16; off > 0; off >>= 1) {
-            const float ob = __shfl_down_sync(0xffffffffu, best, off);
-            const int oi = __shfl_down_sync(0xffffffffu, besti, off);
-            const float os = __shfl_down_sync(0xffffffffu, sum, off);
-            if (ob > best || (ob == best && oi < besti)) { best = ob; besti = oi; }
-            sum += os;
-        }
-        if (lane == 0) { red_best[wid] = best; red_idx[wid] = besti; red_sum[wid] = sum; }
-        __syncthreads();
         if (wid == 0) {
+            // warp 0 finishes the record while the other warps start the next cell (they touch red_* again
+            // only after the next cell's barriers, which warp 0 takes part in)
             best = lane < NWARP ? red_best[lane] : 0.0f;
             besti = lane < NWARP ? red_idx[lane] : 0x7fffffff;
             sum = lane < NWARP ? red_sum[lane] : 0.0f;

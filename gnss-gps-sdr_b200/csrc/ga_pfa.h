@@ -90,23 +90,44 @@ GA_HD int pfa_lag(int t0, int w)
 }
 
 // statistics of one pass-C butterfly (c/search_offline.cpp:190-194: power, FIRST maximum, sum).  The
-// running maximum is tracked by output number w (an immediate in the unrolled code); lags are only
-// formed when the butterfly's maximum is merged into the thread's (best, besti) -- and in the
-// practically unreachable case of two bit-equal powers inside one butterfly.
+// running maximum is tracked by output number w (an immediate in the unrolled code) with a strict
+// compare, branch-free; lags are only formed when the butterfly's maximum is merged into the thread's
+// (best, besti).  `tie` records whether some power was ever bit-equal to the running maximum: only then
+// could "first maximum wins" depend on the order the outputs were produced in, and the caller redoes
+// that butterfly with PfaPeakExact (practically never: exact float ties need degenerate input).
 template <class G>
 struct PfaPeak {
-    float bpw; int bw, t0; float sum;
-    GA_HD void init(int t0_) { bpw = -1.0f; bw = 0; t0 = t0_; sum = 0.0f; }
+    float bpw; int bw, t0; float sum; bool tie;
+    GA_HD void init(int t0_) { bpw = -1.0f; bw = 0; t0 = t0_; sum = 0.0f; tie = false; }
     template <int W_> GA_HD void put(float pw)
     {
-        if (pw > bpw) { bpw = pw; bw = W_; }
-        else if (pw == bpw && pfa_lag<G>(t0, W_) < pfa_lag<G>(t0, bw)) bw = W_;
+        tie = tie || (pw == bpw);
+        const bool gt = pw > bpw;
+        bpw = gt ? pw : bpw;
+        bw = gt ? W_ : bw;
         sum += pw;
     }
     GA_HD void merge(float &best, int &besti, float &tot) const
     {
         const int tau = pfa_lag<G>(t0, bw);
         if (bpw > best || (bpw == best && tau < besti)) { best = bpw; besti = tau; }
+        tot += sum;
+    }
+};
+// the same with the lag compared on every tie (slow path; identical sum order)
+template <class G>
+struct PfaPeakExact {
+    float bpw; int btau, t0; float sum;
+    GA_HD void init(int t0_) { bpw = -1.0f; btau = 0; t0 = t0_; sum = 0.0f; }
+    template <int W_> GA_HD void put(float pw)
+    {
+        const int tau = pfa_lag<G>(t0, W_);
+        if (pw > bpw || (pw == bpw && tau < btau)) { bpw = pw; btau = tau; }
+        sum += pw;
+    }
+    GA_HD void merge(float &best, int &besti, float &tot) const
+    {
+        if (bpw > best || (bpw == best && btau < besti)) { best = bpw; besti = btau; }
         tot += sum;
     }
 };

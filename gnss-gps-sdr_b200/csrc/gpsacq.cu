@@ -47,9 +47,28 @@ typedef Geom<2, 20, 20, 16> H6400;     // L = 12800, W <= 6400 (e.g. 5.456 MHz: 
 enum { HID_4000 = 3, HID_8000 = 4, HID_10000 = 5, HID_6400 = 6 };
 // GRID mode, native W-point prime-factor transforms (ga_pfa.h) for the 1 ms block lengths of the named
 // sampling rates; any other W goes through the embedding above.
-typedef PGeom<16, 11, 31> P5456;       // fs = 5.456 MHz
-typedef PGeom<24, 11, 31> P8184;       // fs = 8.184 MHz
-typedef PGeom<16, 25, 7> P2800;        // fs = 2.8 MHz
+// pass order: which factor runs in pass A (global loads + product), B, C (power + statistics);
+// PFA_ORDER_x permutes the base triple (f0,f1,f2): 0 = (f0,f1,f2), 1 = (f2,f0,f1), 2 = (f1,f2,f0),
+// 3 = (f2,f1,f0), 4 = (f0,f2,f1), 5 = (f1,f0,f2)
+template <int F0, int F1, int F2, int ORDER> struct PermGeom;
+template <int F0, int F1, int F2> struct PermGeom<F0, F1, F2, 0> { typedef PGeom<F0, F1, F2> type; };
+template <int F0, int F1, int F2> struct PermGeom<F0, F1, F2, 1> { typedef PGeom<F2, F0, F1> type; };
+template <int F0, int F1, int F2> struct PermGeom<F0, F1, F2, 2> { typedef PGeom<F1, F2, F0> type; };
+template <int F0, int F1, int F2> struct PermGeom<F0, F1, F2, 3> { typedef PGeom<F2, F1, F0> type; };
+template <int F0, int F1, int F2> struct PermGeom<F0, F1, F2, 4> { typedef PGeom<F0, F2, F1> type; };
+template <int F0, int F1, int F2> struct PermGeom<F0, F1, F2, 5> { typedef PGeom<F1, F0, F2> type; };
+#ifndef PFA_ORDER_5456
+#define PFA_ORDER_5456 2
+#endif
+#ifndef PFA_ORDER_8184
+#define PFA_ORDER_8184 2
+#endif
+#ifndef PFA_ORDER_2800
+#define PFA_ORDER_2800 2
+#endif
+typedef PermGeom<16, 11, 31, PFA_ORDER_5456>::type P5456;    // fs = 5.456 MHz
+typedef PermGeom<24, 11, 31, PFA_ORDER_8184>::type P8184;    // fs = 8.184 MHz
+typedef PermGeom<16, 25, 7, PFA_ORDER_2800>::type P2800;      // fs = 2.8 MHz
 enum { PID_5456 = 7, PID_8184 = 8, PID_2800 = 9 };
 #ifndef PFA_T_5456
 #define PFA_T_5456 128      // 4 warps (a multiple of the 4 sub-partitions keeps the per-thread register budget whole)
@@ -58,16 +77,16 @@ enum { PID_5456 = 7, PID_8184 = 8, PID_2800 = 9 };
 #define PFA_B_5456 4
 #endif
 #ifndef PFA_T_8184
-#define PFA_T_8184 256
+#define PFA_T_8184 128
 #endif
 #ifndef PFA_B_8184
-#define PFA_B_8184 2
+#define PFA_B_8184 3
 #endif
 #ifndef PFA_T_2800
 #define PFA_T_2800 128
 #endif
 #ifndef PFA_B_2800
-#define PFA_B_2800 4
+#define PFA_B_2800 5
 #endif
 
 #define CELL_T_4000 256

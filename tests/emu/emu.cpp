@@ -113,7 +113,7 @@ static void emu_pfa_fwd_t(const cf *x, int conj, cf *out)
 }
 
 template <class G>
-static void emu_pfa_cell_t(const cf *xs, const cf *cs, cf *y, float *best, int *besti, float *sum)
+static void emu_pfa_cell_t(const cf *xs, const cf *cs, cf *y, float *best, int *besti, float *sum, int *n_slow)
 {
     std::vector<cf> sm((size_t)G::SMEM_ELEMS);
     for (int j = 0; j < G::NA; j++) pfa_cell_passA<G>(j, xs, cs, sm.data());
@@ -130,7 +130,14 @@ static void emu_pfa_cell_t(const cf *xs, const cf *cs, cf *y, float *best, int *
             pk.template put<w>(fmaf(v.x, v.x, v.y * v.y));
         });
         for (int w = 0; w < G::RC; w++) y[pfa_lag<G>(t0, w)] = p[w];
-        pk.merge(b, bi, s_);
+        if (!pk.tie) pk.merge(b, bi, s_);
+        else {                                  // what pfa_passC_exact does
+            ++*n_slow;
+            PfaPeakExact<G> pe;
+            pe.init(t0);
+            pfa_passC<G, +1>(j, sm.data(), [&](auto wc, cf v) { pe.template put<decltype(wc)::value>(fmaf(v.x, v.x, v.y * v.y)); });
+            pe.merge(b, bi, s_);
+        }
     }
     *best = b; *besti = bi; *sum = s_;
 }
@@ -196,12 +203,13 @@ int emu_pfa_order(int w, int *k_of_m)
 }
 
 // xs = conj(X), cs = C, both in (a,b,c)-linear order; y: W outputs in natural lag order
-int emu_pfa_cell(int w, const float *xs, const float *cs, float *y, float *best, int *besti, float *sum)
+int emu_pfa_cell(int w, const float *xs, const float *cs, float *y, float *best, int *besti, float *sum, int *n_slow)
 {
+    *n_slow = 0;
     switch (w) {
-    case 5456: emu_pfa_cell_t<P5456>((const cf *)xs, (const cf *)cs, (cf *)y, best, besti, sum); return 0;
-    case 8184: emu_pfa_cell_t<P8184>((const cf *)xs, (const cf *)cs, (cf *)y, best, besti, sum); return 0;
-    case 2800: emu_pfa_cell_t<P2800>((const cf *)xs, (const cf *)cs, (cf *)y, best, besti, sum); return 0;
+    case 5456: emu_pfa_cell_t<P5456>((const cf *)xs, (const cf *)cs, (cf *)y, best, besti, sum, n_slow); return 0;
+    case 8184: emu_pfa_cell_t<P8184>((const cf *)xs, (const cf *)cs, (cf *)y, best, besti, sum, n_slow); return 0;
+    case 2800: emu_pfa_cell_t<P2800>((const cf *)xs, (const cf *)cs, (cf *)y, best, besti, sum, n_slow); return 0;
     }
     return -1;
 }

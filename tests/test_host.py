@@ -191,10 +191,23 @@ def test_pfa_kernel_math_replay_matches_numpy(W):
     inv = np.argsort(order)                                        # natural spectral index -> position
     y = np.fft.ifft(xs.astype(np.complex128)[inv] * cs.astype(np.complex128)[inv]) * W     # conj(X)*C, backward
     yy = np.zeros(W, np.complex64)
-    best, bi, sm = ctypes.c_float(), ctypes.c_int(), ctypes.c_float()
+    best, bi, sm, slow = ctypes.c_float(), ctypes.c_int(), ctypes.c_float(), ctypes.c_int()
     assert L.emu_pfa_cell(W, P(xs.view(np.float32)), P(cs.view(np.float32)), P(yy.view(np.float32)),
-                          ctypes.byref(best), ctypes.byref(bi), ctypes.byref(sm)) == 0
+                          ctypes.byref(best), ctypes.byref(bi), ctypes.byref(sm), ctypes.byref(slow)) == 0
     assert np.abs(yy - y).max() <= 3e-6 * np.abs(y).max()
     pw = np.abs(y) ** 2
-    assert bi.value == int(pw.argmax())
+    assert bi.value == int(pw.argmax()) and slow.value == 0
     assert abs(best.value / pw.max() - 1) < 1e-5 and abs(sm.value / pw.sum() - 1) < 1e-5
+    # exact ties: "first maximum wins" (c/search_offline.cpp:192) must not depend on the order the butterflies
+    # produce their outputs in.  A flat product spectrum gives one peak at lag 0 and exact zeros elsewhere
+    # is not guaranteed in floats, so use the two degenerate inputs whose powers are exactly equal:
+    for fill, want in ((0.0, 0), (1.0, 0)):
+        xs[:] = fill
+        cs[:] = 0.0 if fill == 0.0 else 1.0
+        if fill == 1.0:
+            cs[:] = 0.0
+            cs[np.argsort(order)[0]] = 1.0            # only spectral bin k = 0 set: y[t] = 1 for every lag
+        L.emu_pfa_cell(W, P(xs.view(np.float32)), P(cs.view(np.float32)), P(yy.view(np.float32)),
+                       ctypes.byref(best), ctypes.byref(bi), ctypes.byref(sm), ctypes.byref(slow))
+        assert bi.value == want and slow.value > 0
+        assert best.value == fill and sm.value == fill * W
