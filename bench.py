@@ -286,6 +286,7 @@ def run_engine(args, rank, world, local_rank):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     total_ms, e2e_ms = float(t[0]), float(t[1])
     detected = int((peaks["snr"] >= 25).sum())
+    grid_c4 = None if args.no_grid else grid_c4_sharded(ga, dev, rank, world, dist)      # collective: every rank takes part
 
     if rank == 0:
         peaks_file = ROOT / "MEASURED_PEAKS.json"
@@ -316,6 +317,10 @@ def run_engine(args, rank, world, local_rank):
                 "clocks": clocks,
                 "stage_ms": {k: round(v, 4) for k, v in stage.items()},
                 "detected_prns_last_step": detected}
+        if grid_c4 is not None:
+            grid_c4["contract_gbs"] = grid_c4["value"] * grid_c4["bytes_per_corr"] / 1e9
+            grid_c4["frac_of_hbm_peak_per_gpu"] = grid_c4["contract_gbs"] / world / peak_gbs
+            line["grid_mode_configs4_sharded"] = grid_c4
         if world == 1 and not args.no_grid:
             line["grid_mode_configs1"] = grid_c1_measure(ga, dev, peak_gbs)
         if world == 1 and not args.no_cpu_baseline:
@@ -326,6 +331,63 @@ def run_engine(args, rank, world, local_rank):
     acq.close()
     if world > 1:
         dist.destroy_process_group()
+
+
+def grid_c4_sharded(ga, dev, rank, world, dist):
+    """Secondary: BASELINE.json configs[4] -- ONE acquisition of 32 PRN x 2001 Doppler bins (+-100 kHz @ 100 Hz),
+    fs = 8.184 MHz, 10 ms non-coherent (640,320 coherent correlations), its Doppler grid split into contiguous
+    shards over the ranks (cfg.dop_first/dop_count), one NCCL all-gather of the 32 x 32-byte peak records per
+    acquisition, merged by max snr / lower bin.  STRONG scaling: total work fixed.  Every rank reads the same
+    10,230-byte input.  Timed with CUDA events on the launching stream, max over ranks."""
+    import importlib
+    import torch
+    sg = importlib.import_module("gnss_gps_sdr_b200.siggen")
+    shard = importlib.import_module("gnss_gps_sdr_b200.shard")
+    fs, fc, max_fo, step, K = 8.184e6, 2.046e6, 100000.0, 100.0, 10
+    W = int(round(fs / 1000))
+    nbins = 2 * int(max_fo // step) + 1
+    sats = sg.default_constellation(fs, cn0_dbhz=50.0, seed=1575420002, max_doppler=0.9 * max_fo)
+    bits = sg.synth_capture(W * K, fs, fc, sats, seed=4)
+    lo, n = shard.bin_range(nbins, rank, world)
+    acq = ga.Acquisition(fc, fs, max_fo, device=dev.index, mode=1, doppler_step=step, noncoh_blocks=K, max_blocks=1,
+                         dop_first=lo, dop_count=n)
+    d_bits = torch.from_numpy(bits).to(dev)
+    d_out = torch.zeros(32 * 32, dtype=torch.uint8, device=dev)
+    d_all = torch.zeros(world * 32 * 32, dtype=torch.uint8, device=dev)
+    stream = torch.cuda.current_stream(dev)
+    acq.set_stream(stream.cuda_stream)
+
+    def one():
+        acq.acquire_device(d_bits.data_ptr(), 1, d_out.data_ptr())
+        if world > 1:
+            dist.all_gather_into_tensor(d_all, d_out)
+
+    for _ in range(3):
+        one()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize(dev)
+    reps = 10
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(reps):
+        one()
+    e1.record(stream)
+    torch.cuda.synchronize(dev)
+    t = torch.tensor([e0.elapsed_time(e1) / reps], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t[0])
+    rec = np.frombuffer((d_all if world > 1 else d_out).cpu().numpy().tobytes(), ga.PEAK_DTYPE).reshape(world, 32)
+    merged = shard.merge_peaks(rec)
+    found = sum(1 for s_ in sats if abs(merged[s_["prn"] - 1]["lo_shift"] * step - s_["doppler_hz"]) <= step and merged[s_["prn"] - 1]["snr"] >= 25)
+    out = {"workload": "GRID C4: fs=8.184MHz, 32 PRN x 2001 bins (+-100 kHz @ 100 Hz), 10 ms non-coherent, ONE acquisition "
+                       f"sharded by Doppler bin over {world} GPU(s), NCCL all-gather of the peak records",
+           "value": 32 * nbins * K / ms * 1e3, "unit": UNIT, "scaling": "strong", "ms_per_acquisition": ms,
+           "bins_per_gpu": n, "bytes_per_corr": acq.info["bytes_per_corr"], "generated_svs_found": f"{found}/{len(sats)}",
+           "stage_ms_rank0": {k: round(v, 4) for k, v in acq.stage_times().items()}}
+    acq.close()
+    return out
 
 
 def grid_c1_measure(ga, dev, peak_gbs):

@@ -27,7 +27,7 @@ class _Cfg(C.Structure):
     _fields_ = [("fc", C.c_double), ("fs", C.c_double), ("max_fo", C.c_double),
                 ("fft_len", C.c_int32), ("device", C.c_int32), ("max_blocks", C.c_int32),
                 ("mode", C.c_int32), ("doppler_step", C.c_double), ("noncoh_blocks", C.c_int32),
-                ("reserved", C.c_int32)]
+                ("dop_first", C.c_int32), ("dop_count", C.c_int32), ("reserved", C.c_int32)]
 
 
 class _Info(C.Structure):
@@ -35,7 +35,8 @@ class _Info(C.Structure):
                 ("abi_version", "fft_len", "n1", "n2", "window", "dmax", "n_doppler", "chunk_bytes",
                  "max_blocks", "device", "sm_count", "cell_ctas", "cell_threads", "cell_smem_bytes")] + \
                [("bytes_per_corr", C.c_int64), ("mode", C.c_int32), ("noncoh_blocks", C.c_int32),
-                ("block_bytes", C.c_int32), ("max_acq", C.c_int32), ("doppler_step", C.c_double)]
+                ("block_bytes", C.c_int32), ("max_acq", C.c_int32), ("doppler_step", C.c_double),
+                ("dop_first", C.c_int32), ("n_doppler_full", C.c_int32)]
 
 
 class _Sat(C.Structure):
@@ -80,6 +81,7 @@ def load_library() -> C.CDLL:
         "gpsacq_group_create": (C.c_int, [C.POINTER(_Cfg), C.c_int, i32p, C.c_int, C.POINTER(vp)]),
         "gpsacq_group_destroy": (None, [vp]),
         "gpsacq_group_search_blocks": (C.c_int, [vp, vp, C.c_size_t, vp]),
+        "gpsacq_group_acquire": (C.c_int, [vp, vp, C.c_size_t, vp]),
         "gpsacq_group_gather_kind": (C.c_char_p, [vp]),
         "gpsacq_group_last_error": (C.c_char_p, [vp]),
         "gpsacq_group_engine": (vp, [vp, C.c_int]),
@@ -101,7 +103,7 @@ def load_library() -> C.CDLL:
 ABI_SYMBOLS = ("gpsacq_create", "gpsacq_destroy", "gpsacq_last_error", "gpsacq_get_info",
                "gpsacq_set_stream", "gpsacq_synchronize", "gpsacq_search_blocks",
                "gpsacq_search_blocks_device", "gpsacq_acquire", "gpsacq_acquire_device", "gpsacq_iq8_to_bits", "gpsacq_group_create",
-               "gpsacq_group_destroy", "gpsacq_group_search_blocks", "gpsacq_group_gather_kind", "gpsacq_group_last_error",
+               "gpsacq_group_destroy", "gpsacq_group_search_blocks", "gpsacq_group_acquire", "gpsacq_group_gather_kind", "gpsacq_group_last_error",
                "gpsacq_group_engine", "gpsacq_synth_capture", "gpsacq_stage_times", "gpsacq_get_replica_time",
                "gpsacq_get_replica_spectrum", "gpsacq_get_block_spectrum", "gpsacq_get_cell_stats")
 
@@ -113,11 +115,13 @@ class Acquisition:
     """
 
     def __init__(self, fc: float, fs: float, max_fo: float = 5000.0, device: int = -1, max_blocks: int = 0,
-                 mode: int = 0, doppler_step: float = 0.0, noncoh_blocks: int = 1):
+                 mode: int = 0, doppler_step: float = 0.0, noncoh_blocks: int = 1, dop_first: int = 0, dop_count: int = 0):
+        """dop_first/dop_count (GRID mode): search only that contiguous shard of the Doppler grid -- records keep
+        absolute bin numbers, shards are merged with shard.merge_peaks()."""
         self._lib = load_library()
         self._h = C.c_void_p()
         cfg = _Cfg(fc=fc, fs=fs, max_fo=max_fo, fft_len=0, device=device, max_blocks=max_blocks, mode=mode,
-                   doppler_step=doppler_step, noncoh_blocks=noncoh_blocks, reserved=0)
+                   doppler_step=doppler_step, noncoh_blocks=noncoh_blocks, dop_first=dop_first, dop_count=dop_count, reserved=0)
         rc = self._lib.gpsacq_create(C.byref(cfg), C.byref(self._h))
         if rc != 0:
             msg = self._lib.gpsacq_last_error(None)
@@ -265,15 +269,21 @@ def synth_capture_gpu(n_samples: int, fs: float, fc: float, sats, seed: int = 1,
 
 
 class AcquisitionGroup:
-    """Several GPUs in one process (REF mode): contiguous chunk ranges per device, one ncclAllGather of the
-    peak records per batch (include/gpsacq.h, gpsacq_group_*)."""
+    """Several GPUs in one process: REF mode splits the chunks of a batch, GRID mode splits the Doppler bins of
+    every acquisition; one ncclAllGather of the peak records per batch (include/gpsacq.h, gpsacq_group_*).
+    `devices` may name a device more than once (then the records are gathered through the host)."""
 
-    def __init__(self, fc: float, fs: float, max_fo: float = 5000.0, n_gpus: int = 2, use_nccl: bool = True, max_blocks: int = 0):
+    def __init__(self, fc: float, fs: float, max_fo: float = 5000.0, n_gpus: int = 2, use_nccl: bool = True, max_blocks: int = 0,
+                 mode: int = 0, doppler_step: float = 0.0, noncoh_blocks: int = 1, devices=None):
         self._lib = load_library()
         self._g = C.c_void_p()
-        cfg = _Cfg(fc=fc, fs=fs, max_fo=max_fo, fft_len=0, device=-1, max_blocks=max_blocks, mode=0, doppler_step=0.0,
-                   noncoh_blocks=1, reserved=0)
-        rc = self._lib.gpsacq_group_create(C.byref(cfg), n_gpus, None, 1 if use_nccl else 0, C.byref(self._g))
+        cfg = _Cfg(fc=fc, fs=fs, max_fo=max_fo, fft_len=0, device=-1, max_blocks=max_blocks, mode=mode, doppler_step=doppler_step,
+                   noncoh_blocks=noncoh_blocks, dop_first=0, dop_count=0, reserved=0)
+        devs = None
+        if devices is not None:
+            devs = (C.c_int32 * n_gpus)(*devices)
+        self.acq_bytes = int(round(fs / 1000)) // 8 * noncoh_blocks
+        rc = self._lib.gpsacq_group_create(C.byref(cfg), n_gpus, devs, 1 if use_nccl else 0, C.byref(self._g))
         if rc != 0:
             msg = self._lib.gpsacq_last_error(None)
             raise GpsAcqError(f"gpsacq_group_create failed ({rc}): {msg.decode() if msg else '?'}")
@@ -287,6 +297,16 @@ class AcquisitionGroup:
         rc = self._lib.gpsacq_group_search_blocks(self._g, buf.ctypes.data, n, out.ctypes.data)
         if rc != 0:
             raise GpsAcqError(f"group search failed ({rc}): {self._lib.gpsacq_group_last_error(self._g).decode()}")
+        return out
+
+    def acquire(self, bits) -> np.ndarray:
+        """GRID group: 32 records per acquisition, identical to a single-GPU handle's."""
+        buf = np.ascontiguousarray(np.frombuffer(bits, dtype=np.uint8) if not isinstance(bits, np.ndarray) else bits, dtype=np.uint8)
+        n = buf.size // self.acq_bytes
+        out = np.zeros(n * 32, dtype=PEAK_DTYPE)
+        rc = self._lib.gpsacq_group_acquire(self._g, buf.ctypes.data, n, out.ctypes.data)
+        if rc != 0:
+            raise GpsAcqError(f"group acquire failed ({rc}): {self._lib.gpsacq_group_last_error(self._g).decode()}")
         return out
 
     def close(self):

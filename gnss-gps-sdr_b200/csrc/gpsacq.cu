@@ -113,6 +113,7 @@ struct gpsacq {
     int gid, n, n1, n2, w, dmax, ndop, chunk_bytes, chunk_samples, cap, device, sm_count;
     int cell_ctas, cell_threads, cell_smem, cell_nw;
     int mode, kblocks, wipe_m, block_bytes, cap_acq;
+    int dmax_full, dop_first;          // GRID shard: h->dmax is dmax_full - dop_first, so that bin = index - h->dmax is absolute
     double step;
     cf *d_wipe, *d_xg;
     float *d_code_w;
@@ -524,12 +525,20 @@ static int create_grid(gpsacq *h)
     if (fabs(md - h->wipe_m) > 1e-6 * md) { h->err = "GRID mode needs FS/doppler_step to be an integer"; return GPSACQ_EINVAL; }
     h->kblocks = c.noncoh_blocks > 0 ? c.noncoh_blocks : 1;
     h->step = c.doppler_step;
-    h->dmax = (int)floor(c.max_fo / c.doppler_step + 1e-9);
-    h->ndop = 2 * h->dmax + 1;
+    h->dmax_full = (int)floor(c.max_fo / c.doppler_step + 1e-9);
+    const int ndop_full = 2 * h->dmax_full + 1;
+    h->dop_first = 0;
+    h->ndop = ndop_full;
+    if (c.dop_count != 0) {          // a shard of the Doppler grid
+        if (c.dop_first < 0 || c.dop_count < 0 || (long long)c.dop_first + c.dop_count > ndop_full) { h->err = "dop_first/dop_count outside the Doppler grid"; return GPSACQ_EINVAL; }
+        h->dop_first = c.dop_first;
+        h->ndop = c.dop_count;
+    }
+    h->dmax = h->dmax_full - h->dop_first;      // kernels form the absolute bin as index - h->dmax
     h->block_bytes = h->w / 8;
     h->chunk_bytes = h->block_bytes * h->kblocks;
     h->chunk_samples = h->w;
-    const int pgid = pfa_gid_for(h->w, h->dmax);
+    const int pgid = pfa_gid_for(h->w, h->dmax_full);
     if (pgid >= 0) { h->gid = pgid; h->n1 = 1; h->n2 = h->w; h->cell_nw = 0; }
     else if (h->w <= H4000::N2) { h->gid = HID_4000; h->n1 = 2; h->n2 = H4000::N2; h->cell_nw = h->w <= 7 * H4000::OUT_STRIDE ? 7 : 10; }
     else if (h->w <= H6400::N2) { h->gid = HID_6400; h->n1 = 2; h->n2 = H6400::N2; h->cell_nw = h->w <= 14 * H6400::OUT_STRIDE ? 14 : 16; }
@@ -672,7 +681,9 @@ int gpsacq_get_info(const gpsacq_t *h, gpsacq_info *info)
     memset(info, 0, sizeof *info);
     info->abi_version = GPSACQ_ABI_VERSION;
     info->fft_len = h->n; info->n1 = h->n1; info->n2 = h->n2;
-    info->window = h->w; info->dmax = h->dmax; info->n_doppler = h->ndop;
+    info->window = h->w; info->dmax = h->mode == GPSACQ_MODE_GRID ? h->dmax_full : h->dmax; info->n_doppler = h->ndop;
+    info->dop_first = h->mode == GPSACQ_MODE_GRID ? h->dop_first : 0;
+    info->n_doppler_full = h->mode == GPSACQ_MODE_GRID ? 2 * h->dmax_full + 1 : h->ndop;
     info->chunk_bytes = h->chunk_bytes; info->max_blocks = h->cap;
     info->device = h->device; info->sm_count = h->sm_count;
     info->cell_ctas = h->cell_ctas; info->cell_threads = h->cell_threads; info->cell_smem_bytes = h->cell_smem;
@@ -970,7 +981,13 @@ void gpsacq_group_destroy(gpsacq_group_t *g)
 
 int gpsacq_group_create(const gpsacq_cfg *cfg, int n_gpus, const int32_t *devices, int use_nccl, gpsacq_group_t **out)
 {
-    if (!cfg || !out || n_gpus < 1 || cfg->mode != GPSACQ_MODE_REF) { g_create_error = "gpsacq_group_create: bad arguments (REF mode only)"; return GPSACQ_EINVAL; }
+    if (!cfg || !out || n_gpus < 1 || (cfg->mode != GPSACQ_MODE_REF && cfg->mode != GPSACQ_MODE_GRID)) { g_create_error = "gpsacq_group_create: bad arguments"; return GPSACQ_EINVAL; }
+    int ndop_full = 0;
+    if (cfg->mode == GPSACQ_MODE_GRID) {
+        if (!(cfg->doppler_step > 0) || cfg->dop_count != 0) { g_create_error = "gpsacq_group_create: GRID needs doppler_step > 0 and an unsharded cfg"; return GPSACQ_EINVAL; }
+        ndop_full = 2 * (int)floor(cfg->max_fo / cfg->doppler_step + 1e-9) + 1;
+        if (n_gpus > ndop_full) { g_create_error = "gpsacq_group_create: more GPUs than Doppler bins"; return GPSACQ_EINVAL; }
+    }
     *out = nullptr;
     gpsacq_group *g = new (std::nothrow) gpsacq_group();
     if (!g) return GPSACQ_ENOMEM;
@@ -978,6 +995,10 @@ int gpsacq_group_create(const gpsacq_cfg *cfg, int n_gpus, const int32_t *device
     for (int i = 0; i < n_gpus; i++) {
         gpsacq_cfg c = *cfg;
         c.device = devices ? devices[i] : i;
+        if (cfg->mode == GPSACQ_MODE_GRID) {      // contiguous, balanced bin ranges in ascending order
+            c.dop_first = (int)((long long)ndop_full * i / n_gpus);
+            c.dop_count = (int)((long long)ndop_full * (i + 1) / n_gpus) - c.dop_first;
+        }
         gpsacq *h = nullptr;
         const int rc = gpsacq_create(&c, &h);
         if (rc) { gpsacq_group_destroy(g); return rc; }
@@ -985,6 +1006,11 @@ int gpsacq_group_create(const gpsacq_cfg *cfg, int n_gpus, const int32_t *device
         g->dev.push_back(h->device);
     }
     g->cap = g->eng[0]->cap;
+    if (cfg->mode == GPSACQ_MODE_GRID) {          // records per device and batch: 32 per acquisition
+        int cap_acq = g->eng[0]->cap_acq;
+        for (gpsacq *h : g->eng) cap_acq = std::min(cap_acq, h->cap_acq);
+        g->cap = cap_acq * 32;
+    }
     g->sv.resize(n_gpus);
     g->d_all.assign(n_gpus, nullptr);
     for (int i = 0; i < n_gpus; i++) {
@@ -1052,6 +1078,60 @@ int gpsacq_group_search_blocks(gpsacq_group_t *g, const uint8_t *bits, size_t n_
             }
         }
         done += nb;
+    }
+    return GPSACQ_OK;
+}
+
+int gpsacq_group_acquire(gpsacq_group_t *g, const uint8_t *bits, size_t n_acq, gpsacq_peak *out)
+{
+    if (!g || (!bits && n_acq) || (!out && n_acq)) return GPSACQ_EINVAL;
+    if (g->eng[0]->mode != GPSACQ_MODE_GRID) { g->err = "gpsacq_group_acquire needs a GPSACQ_MODE_GRID group"; return GPSACQ_EINVAL; }
+    const size_t ng = g->eng.size(), cap_acq = (size_t)g->cap / 32, acq_bytes = (size_t)g->eng[0]->chunk_bytes;
+    for (size_t done = 0; done < n_acq;) {
+        const size_t na = std::min(cap_acq, n_acq - done), nrec = na * 32;
+        // every device gets the whole (tiny) input and searches its own Doppler bins
+        for (size_t d = 0; d < ng; d++) {
+            gpsacq *h = g->eng[d];
+            if (cudaSetDevice(h->device) != cudaSuccess) { g->err = "cudaSetDevice failed"; return GPSACQ_ECUDA; }
+            memcpy(h->h_bits, bits + done * acq_bytes, na * acq_bytes);
+            if (cudaMemcpyAsync(h->d_bits, h->h_bits, na * acq_bytes, cudaMemcpyHostToDevice, h->stream) != cudaSuccess) { g->err = "H2D copy failed"; return GPSACQ_ECUDA; }
+            const int rc = acquire_device_impl(h, h->d_bits, na, (gpsacq_peak *)h->d_peaks);
+            if (rc) { g->err = h->err; return rc; }
+        }
+        if (g->use_nccl) {
+            g->nccl.GroupStart();
+            for (size_t d = 0; d < ng; d++) {
+                cudaSetDevice(g->dev[d]);
+                g->nccl.AllGather(g->eng[d]->d_peaks, g->d_all[d], (size_t)g->cap * sizeof(Peak), 0 /*ncclInt8*/, g->comm[d], g->eng[d]->stream);
+            }
+            const ncclResult_t r = g->nccl.GroupEnd();
+            if (r != 0) { g->err = std::string("ncclAllGather: ") + (g->nccl.GetErrorString ? g->nccl.GetErrorString(r) : "error"); return GPSACQ_ECUDA; }
+            cudaSetDevice(g->dev[0]);
+            if (cudaMemcpyAsync(g->h_all.data(), g->d_all[0], ng * (size_t)g->cap * sizeof(Peak), cudaMemcpyDeviceToHost, g->eng[0]->stream) != cudaSuccess) { g->err = "D2H failed"; return GPSACQ_ECUDA; }
+            for (size_t d = 0; d < ng; d++) { cudaSetDevice(g->dev[d]); if (cudaStreamSynchronize(g->eng[d]->stream) != cudaSuccess) { g->err = "stream sync failed"; return GPSACQ_ECUDA; } }
+        } else {
+            for (size_t d = 0; d < ng; d++) {
+                gpsacq *h = g->eng[d];
+                cudaSetDevice(h->device);
+                if (cudaMemcpyAsync(h->h_peaks, h->d_peaks, nrec * sizeof(Peak), cudaMemcpyDeviceToHost, h->stream) != cudaSuccess) { g->err = "D2H failed"; return GPSACQ_ECUDA; }
+            }
+            for (size_t d = 0; d < ng; d++) {
+                gpsacq *h = g->eng[d];
+                cudaSetDevice(h->device);
+                if (cudaStreamSynchronize(h->stream) != cudaSuccess) { g->err = "stream sync failed"; return GPSACQ_ECUDA; }
+                memcpy(g->h_all.data() + d * (size_t)g->cap, h->h_peaks, nrec * sizeof(Peak));
+            }
+        }
+        // merge: devices hold ascending bin ranges, so "strictly greater" keeps the lower bin on equal snr
+        for (size_t r = 0; r < nrec; r++) {
+            Peak best = g->h_all[r];
+            for (size_t d = 1; d < ng; d++) {
+                const Peak &p = g->h_all[d * (size_t)g->cap + r];
+                if (p.snr > best.snr) best = p;
+            }
+            memcpy(out + done * 32 + r, &best, sizeof(Peak));
+        }
+        done += na;
     }
     return GPSACQ_OK;
 }

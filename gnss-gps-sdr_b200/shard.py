@@ -36,5 +36,36 @@ def gather_peaks(local_u8, n_runs: int, world: int, group=None):
     return torch.cat(parts)
 
 
+# ---- GRID mode: ONE acquisition's (PRN x Doppler) grid split by Doppler bin ----------------------------
+def bin_range(n_bins: int, rank: int, world: int) -> tuple[int, int]:
+    """(dop_first, dop_count) of rank's contiguous shard of the n_bins-bin Doppler grid -- the same split as
+    gpsacq_group_create() (ascending ranges, so a lower rank always holds lower bins)."""
+    lo = n_bins * rank // world
+    return lo, n_bins * (rank + 1) // world - lo
+
+
+def merge_peaks(per_rank: np.ndarray) -> np.ndarray:
+    """per_rank[r, i] = record i of rank r (rank order = ascending bin ranges).  Keeps, per record, the
+    shard with the highest snr; on equal snr the lowest rank, i.e. the lower Doppler bin -- exactly the
+    winner of the reference's ascending strictly-greater scan (c/search_offline.cpp:173,198)."""
+    per_rank = np.asarray(per_rank)
+    best = per_rank[0].copy()
+    for r in range(1, per_rank.shape[0]):
+        take = per_rank[r]["snr"] > best["snr"]
+        best[take] = per_rank[r][take]
+    return best
+
+
+def gather_merge_peaks(local_u8, world: int, dtype, group=None) -> np.ndarray:
+    """All-gather every rank's records for the same acquisitions (uint8 tensor, CUDA -> NCCL, CPU -> gloo)
+    and merge them with merge_peaks()."""
+    import torch
+    import torch.distributed as dist
+    out = torch.empty(world * local_u8.numel(), dtype=torch.uint8, device=local_u8.device)
+    dist.all_gather_into_tensor(out, local_u8.contiguous(), group=group)
+    rec = np.frombuffer(out.cpu().numpy().tobytes(), dtype=dtype).reshape(world, -1)
+    return merge_peaks(rec)
+
+
 def peaks_from_bytes(buf, dtype) -> np.ndarray:
     return np.frombuffer(bytes(buf), dtype=dtype)

@@ -51,7 +51,7 @@
 extern "C" {
 #endif
 
-#define GPSACQ_ABI_VERSION 2
+#define GPSACQ_ABI_VERSION 3
 
 #define GPSACQ_OK        0
 #define GPSACQ_EINVAL   (-1)   /* bad argument / unsupported configuration        */
@@ -75,7 +75,10 @@ typedef struct gpsacq_cfg {
     int32_t mode;        /* GPSACQ_MODE_REF (0, the reference's semantics) or GPSACQ_MODE_GRID      */
     double  doppler_step;/* GRID only: Doppler bin spacing in Hz; FS/doppler_step must be an integer */
     int32_t noncoh_blocks;/* GRID only: K = number of 1 ms blocks summed non-coherently (>= 1)       */
-    int32_t reserved;
+    int32_t dop_first;   /* GRID only: search just the bins [dop_first, dop_first + dop_count) of the     */
+    int32_t dop_count;   /*   n_doppler-bin grid (index 0 = bin -dmax).  dop_count = 0: the whole grid.    */
+    int32_t reserved;    /*   This is how the (PRN x Doppler) grid of ONE acquisition is sharded over GPUs: */
+                         /*   records keep absolute bin numbers, so shards merge by max snr / lower bin.    */
 } gpsacq_cfg;
 
 #define GPSACQ_MODE_REF  0   /* N = 40000 coherent window, bins of FS/N, one chunk per PRN
@@ -128,6 +131,8 @@ typedef struct gpsacq_info {
     int32_t block_bytes;   /* GRID: bytes per 1 ms block = window/8                */
     int32_t max_acq;       /* GRID: acquisitions per internal batch                */
     double  doppler_step;  /* Hz between Doppler bins (REF: FS/fft_len)            */
+    int32_t dop_first;     /* GRID: first bin of this handle's shard (0 = bin -dmax); n_doppler = bins in the shard */
+    int32_t n_doppler_full;/* bins of the whole grid, 2*dmax+1                                    */
 } gpsacq_info;
 
 /* Number of kernels this library launches for a batch (for bench.py's gpu_launches). */
@@ -173,17 +178,23 @@ int  gpsacq_acquire_device(gpsacq_t *h, const uint8_t *d_packed_bits, size_t n_a
 int  gpsacq_iq8_to_bits(gpsacq_t *h, const void *iq, size_t n_samples, int format, double shift_hz,
                         double fs, uint8_t *bits_out);
 
-/* ---- several GPUs in one process (REF mode) ----------------------------------------------------
- * One engine per device; a batch's chunks are split into contiguous ranges (chunk b keeps PRN b mod 32),
- * every device searches its range, and the 32-byte peak records are exchanged with ONE collective per
- * batch: ncclAllGather over NVLink (NCCL is dlopen'ed -- libnccl.so.2 -- so the library has no link-time
- * dependency on it; if it cannot be loaded, or use_nccl = 0, the records are gathered through the host).
- * No collective touches the data path.  gpsacq_group_gather_kind() says which gather is active. */
+/* ---- several GPUs in one process ------------------------------------------------------------------
+ * One engine per device.  REF mode: a batch's chunks are split into contiguous ranges (chunk b keeps PRN
+ * b mod 32) and every device searches its range.  GRID mode: the Doppler bins of the grid are split into
+ * contiguous ranges (cfg.dop_first/dop_count per device), every device searches all 32 PRNs of every
+ * acquisition over its bins, and the per-device winners are merged (higher snr; equal snr -> lower bin,
+ * the reference's ascending strictly-greater scan, c/search_offline.cpp:198).  Either way the 32-byte peak
+ * records are exchanged with ONE collective per batch: ncclAllGather over NVLink (NCCL is dlopen'ed --
+ * libnccl.so.2 -- so the library has no link-time dependency on it; if it cannot be loaded, or
+ * use_nccl = 0, the records are gathered through the host).  No collective touches the data path.
+ * gpsacq_group_gather_kind() says which gather is active. */
 typedef struct gpsacq_group gpsacq_group_t;
 int  gpsacq_group_create(const gpsacq_cfg *cfg, int n_gpus, const int32_t *devices /* NULL: 0..n-1 */,
                          int use_nccl, gpsacq_group_t **out);
 void gpsacq_group_destroy(gpsacq_group_t *g);
 int  gpsacq_group_search_blocks(gpsacq_group_t *g, const uint8_t *packed_bits, size_t n_blocks, gpsacq_peak *out);
+/* GRID group: like gpsacq_acquire(); out receives 32 records per acquisition, identical to a single-GPU handle's. */
+int  gpsacq_group_acquire(gpsacq_group_t *g, const uint8_t *packed_bits, size_t n_acq, gpsacq_peak *out);
 const char *gpsacq_group_gather_kind(const gpsacq_group_t *g);   /* "nccl" or "host" */
 const char *gpsacq_group_last_error(const gpsacq_group_t *g);
 gpsacq_t *gpsacq_group_engine(gpsacq_group_t *g, int i);         /* engine of the i-th device (for info/probes) */

@@ -91,6 +91,42 @@ def test_grid_native_transform_matches_embedding(ga, siggen, monkeypatch, fs, fc
         assert (ca["max_idx"] != cb["max_idx"]).sum() <= 1
 
 
+def test_grid_doppler_shards_merge_to_the_full_grid(ga, siggen):
+    """Multi-GPU sharding of ONE acquisition's (PRN x Doppler) grid: handles restricted to contiguous bin
+    ranges (cfg.dop_first/dop_count) merged with shard.merge_peaks() == the unsharded handle, bit for bit;
+    the one-process group API (here both shards on the same device, host gather) gives the same records."""
+    shard = importlib.import_module("gnss_gps_sdr_b200.shard")
+    fs, fc, K = 2.8e6, 0.62e6, 2
+    W = int(round(fs / 1000))
+    sats = siggen.default_constellation(fs, cn0_dbhz=50.0, seed=9, max_doppler=9000.0)
+    bits = siggen.synth_capture(W * K * 2, fs, fc, sats, seed=13)
+    full = ga.Acquisition(fc, fs, 10000.0, mode=1, doppler_step=250.0, noncoh_blocks=K)
+    try:
+        want = full.acquire(bits).copy()
+        nb = full.info["n_doppler"]
+        assert full.info["n_doppler_full"] == nb == 81 and full.info["dop_first"] == 0
+    finally:
+        full.close()
+    for world in (2, 3):
+        parts = []
+        for r in range(world):
+            lo, n = shard.bin_range(nb, r, world)
+            h = ga.Acquisition(fc, fs, 10000.0, mode=1, doppler_step=250.0, noncoh_blocks=K, dop_first=lo, dop_count=n)
+            try:
+                assert h.info["n_doppler"] == n and h.info["dop_first"] == lo and h.info["n_doppler_full"] == nb
+                parts.append(h.acquire(bits).copy())
+            finally:
+                h.close()
+        assert shard.merge_peaks(np.stack(parts)).tobytes() == want.tobytes()
+    grp = ga.AcquisitionGroup(fc, fs, 10000.0, n_gpus=2, use_nccl=False, mode=1, doppler_step=250.0, noncoh_blocks=K, devices=[0, 0])
+    try:
+        assert grp.acquire(bits).tobytes() == want.tobytes()
+    finally:
+        grp.close()
+    with pytest.raises(ga.GpsAcqError, match="outside"):
+        ga.Acquisition(fc, fs, 10000.0, mode=1, doppler_step=250.0, dop_first=80, dop_count=5)
+
+
 def test_grid_agrees_with_ref_mode_on_the_capture(ga, engines_ref=None):
     """on the Nottingham capture GRID (1 ms, 500 Hz) finds the strong SVs of REF mode at
     the same code phase (+-1 sample) and within one 500 Hz step."""
