@@ -44,8 +44,17 @@ class _Sat(C.Structure):
                 ("code_phase_chips", C.c_double), ("carrier_phase_cycles", C.c_double)]
 
 
+class _Handoff(C.Structure):
+    _fields_ = [("lo_dop_hz", C.c_double), ("ca_dop_hz", C.c_double), ("lo_rate", C.c_uint32), ("ca_rate", C.c_uint32),
+                ("ca_shift", C.c_int32), ("ca_pause", C.c_uint32), ("taps", C.c_int32), ("sv", C.c_int32)]
+
+
+HANDOFF_DTYPE = np.dtype([("lo_dop_hz", "<f8"), ("ca_dop_hz", "<f8"), ("lo_rate", "<u4"), ("ca_rate", "<u4"),
+                          ("ca_shift", "<i4"), ("ca_pause", "<u4"), ("taps", "<i4"), ("sv", "<i4")])
+
 PEAK_DTYPE = np.dtype([("snr", "<f4"), ("max_pwr", "<f4"), ("tot_pwr", "<f4"), ("lo_shift", "<i4"),
                        ("ca_shift", "<i4"), ("sv", "<i4"), ("flags", "<i4"), ("reserved", "<i4")])
+EVENT_DTYPE = np.dtype([("chunk_index", "<i8"), ("sv", "<i4"), ("ch", "<i4"), ("peak", PEAK_DTYPE), ("start", HANDOFF_DTYPE)])
 CELL_DTYPE = np.dtype([("max_pwr", "<f4"), ("tot_pwr", "<f4"), ("max_idx", "<i4"), ("reserved", "<i4")])
 
 _LIB = None
@@ -85,6 +94,14 @@ def load_library() -> C.CDLL:
         "gpsacq_group_gather_kind": (C.c_char_p, [vp]),
         "gpsacq_group_last_error": (C.c_char_p, [vp]),
         "gpsacq_group_engine": (vp, [vp, C.c_int]),
+        "gpsacq_handoff_compute": (C.c_int, [vp, C.c_double, C.c_double, C.c_double, C.c_double, C.c_double, vp]),
+        "gpsacq_service_create": (C.c_int, [vp, C.c_int, C.c_int, C.POINTER(vp)]),
+        "gpsacq_service_destroy": (None, [vp]),
+        "gpsacq_service_feed": (C.c_int, [vp, vp, C.c_size_t, C.POINTER(C.c_size_t), vp, C.c_size_t, C.POINTER(C.c_size_t)]),
+        "gpsacq_service_enable": (C.c_int, [vp, C.c_int]),
+        "gpsacq_service_signal_lost": (C.c_int, [vp, C.c_int]),
+        "gpsacq_service_state": (C.c_int, [vp, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), C.POINTER(C.c_int64)]),
+        "gpsacq_service_last_error": (C.c_char_p, [vp]),
         "gpsacq_synth_capture": (C.c_int, [C.c_int, C.c_double, C.c_double, C.POINTER(_Sat), C.c_int, C.c_double, C.c_double,
                                            C.c_uint64, C.c_size_t, vp, vp]),
         "gpsacq_stage_times": (C.c_int, [vp, f32p]),
@@ -104,7 +121,9 @@ ABI_SYMBOLS = ("gpsacq_create", "gpsacq_destroy", "gpsacq_last_error", "gpsacq_g
                "gpsacq_set_stream", "gpsacq_synchronize", "gpsacq_search_blocks",
                "gpsacq_search_blocks_device", "gpsacq_acquire", "gpsacq_acquire_device", "gpsacq_iq8_to_bits", "gpsacq_group_create",
                "gpsacq_group_destroy", "gpsacq_group_search_blocks", "gpsacq_group_acquire", "gpsacq_group_gather_kind", "gpsacq_group_last_error",
-               "gpsacq_group_engine", "gpsacq_synth_capture", "gpsacq_stage_times", "gpsacq_get_replica_time",
+               "gpsacq_group_engine", "gpsacq_handoff_compute", "gpsacq_service_create", "gpsacq_service_destroy",
+               "gpsacq_service_feed", "gpsacq_service_enable", "gpsacq_service_signal_lost", "gpsacq_service_state",
+               "gpsacq_service_last_error", "gpsacq_synth_capture", "gpsacq_stage_times", "gpsacq_get_replica_time",
                "gpsacq_get_replica_spectrum", "gpsacq_get_block_spectrum", "gpsacq_get_cell_stats")
 
 
@@ -266,6 +285,68 @@ def synth_capture_gpu(n_samples: int, fs: float, fc: float, sats, seed: int = 1,
         msg = lib.gpsacq_last_error(None)
         raise GpsAcqError(f"gpsacq_synth_capture failed ({rc}): {msg.decode() if msg else '?'}")
     return out
+
+
+def handoff(peak, fc: float, fs: float, bin_num: float, bin_den: float, secs_since_sample: float) -> np.ndarray:
+    """CHANNEL::Start() values for one acquisition record (c/channel.cpp:134-171); needs no GPU.
+    Doppler = lo_shift*bin_num/bin_den: (FS, FFT_LEN) in REF mode, (doppler_step, 1) in GRID mode."""
+    lib = load_library()
+    rec = np.zeros(1, PEAK_DTYPE)
+    rec[0] = peak
+    out = np.zeros(1, HANDOFF_DTYPE)
+    rc = lib.gpsacq_handoff_compute(rec.ctypes.data, fc, fs, bin_num, bin_den, secs_since_sample, out.ctypes.data)
+    if rc != 0:
+        raise GpsAcqError(f"gpsacq_handoff_compute failed ({rc})")
+    return out[0]
+
+
+class SearchService:
+    """The receiver's SearchTask() loop over a chunk stream (c/search.cpp:214-239): skip tracked SVs, one chunk per
+    searched SV, channel allocation, detection events with their CHANNEL::Start() hand-off (include/gpsacq.h,
+    gpsacq_service_*)."""
+
+    def __init__(self, acq: Acquisition, num_chans: int = 0, max_rounds_per_batch: int = 0):
+        self._lib = load_library()
+        self._acq = acq
+        self._s = C.c_void_p()
+        rc = self._lib.gpsacq_service_create(acq._h, num_chans, max_rounds_per_batch, C.byref(self._s))
+        if rc != 0:
+            raise GpsAcqError(f"gpsacq_service_create failed ({rc}): {self._lib.gpsacq_last_error(acq._h).decode()}")
+
+    def feed(self, chunks, max_events: int = 64):
+        """Returns (chunks consumed, EVENT_DTYPE records)."""
+        buf = np.ascontiguousarray(np.frombuffer(chunks, dtype=np.uint8) if not isinstance(chunks, np.ndarray) else chunks, dtype=np.uint8)
+        n = buf.size // self._acq.chunk_bytes
+        ev = np.zeros(max_events, EVENT_DTYPE)
+        used, nev = C.c_size_t(), C.c_size_t()
+        rc = self._lib.gpsacq_service_feed(self._s, buf.ctypes.data, n, C.byref(used), ev.ctypes.data, max_events, C.byref(nev))
+        if rc != 0:
+            raise GpsAcqError(f"gpsacq_service_feed failed ({rc}): {self._lib.gpsacq_service_last_error(self._s).decode()}")
+        return used.value, ev[: nev.value].copy()
+
+    def enable(self, sv: int):
+        if self._lib.gpsacq_service_enable(self._s, sv) != 0:
+            raise GpsAcqError("bad sv")
+
+    def signal_lost(self, ch: int):
+        if self._lib.gpsacq_service_signal_lost(self._s, ch) != 0:
+            raise GpsAcqError("bad channel")
+
+    def state(self):
+        a, b, c = C.c_uint32(), C.c_uint32(), C.c_int64()
+        self._lib.gpsacq_service_state(self._s, C.byref(a), C.byref(b), C.byref(c))
+        return a.value, b.value, c.value
+
+    def close(self):
+        if self._s and self._s.value:
+            self._lib.gpsacq_service_destroy(self._s)
+            self._s = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 class AcquisitionGroup:

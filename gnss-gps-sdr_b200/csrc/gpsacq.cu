@@ -1137,3 +1137,5 @@ int gpsacq_group_acquire(gpsacq_group_t *g, const uint8_t *bits, size_t n_acq, g
 }
 
 }  // extern "C" (group)
+
+#include "ga_service.h"

@@ -199,6 +199,52 @@ const char *gpsacq_group_gather_kind(const gpsacq_group_t *g);   /* "nccl" or "h
 const char *gpsacq_group_last_error(const gpsacq_group_t *g);
 gpsacq_t *gpsacq_group_engine(gpsacq_group_t *g, int i);         /* engine of the i-th device (for info/probes) */
 
+/* ---- acquisition -> tracking hand-off --------------------------------------
+ * What CHANNEL::Start() (c/channel.cpp:134-171) derives from an acquisition record before it programs a tracking
+ * channel: Doppler from the bin shift, 32-bit carrier / code NCO rate words, the code phase corrected for the code
+ * creep since the sample was taken, the code-generator pause, and the Gold-code tap word (T1<<4)+T2 that
+ * SearchTask() passes to ChanStart() (c/search.cpp:236-237).  Doppler = lo_shift*bin_num/bin_den, evaluated in that
+ * order like :147: (bin_num, bin_den) = (FS, FFT_LEN) in REF mode, (doppler_step, 1) in GRID mode. */
+typedef struct gpsacq_handoff {
+    double   lo_dop_hz;    /* lo_shift*FS/FFT_LEN                        (:147) */
+    double   ca_dop_hz;    /* lo_dop/L1*CPS                              (:148) */
+    uint32_t lo_rate;      /* (FC+lo_dop)/FS*2^32                        (:151) */
+    uint32_t ca_rate;      /* (CPS+ca_dop)/FS*2^32                       (:152) */
+    int32_t  ca_shift;     /* + nearbyint(ca_dop*secs*FS/CPS)            (:161) */
+    uint32_t ca_pause;     /* (2W - ca_shift) % W, W = samples per ms    (:164) */
+    int32_t  taps;         /* (T1<<4)+T2                                        */
+    int32_t  sv;
+} gpsacq_handoff;
+int  gpsacq_handoff_compute(const gpsacq_peak *p, double fc, double fs, double bin_num, double bin_den,
+                            double secs_since_sample, gpsacq_handoff *out);
+
+/* ---- streaming / re-acquisition service loop -------------------------------
+ * The receiver's SearchTask() (c/search.cpp:214-239) over a stream of chunks: round-robin over the SVs that are
+ * not being tracked (Busy[], SearchEnable()), ONE fresh chunk per searched SV, nothing sampled while all
+ * num_chans channels are busy (ChanReset()), detection (snr >= 25) marks the SV busy and starts a channel.
+ * Chunks are searched in GPU batches, speculatively (see csrc/ga_service.h); the event sequence is exactly the
+ * one-chunk-at-a-time loop's.  REF-mode handle; the handle must outlive the service. */
+typedef struct gpsacq_service gpsacq_service_t;
+typedef struct gpsacq_event {
+    int64_t        chunk_index;  /* which Sample() of the stream (0-based, counted over all feed() calls) */
+    int32_t        sv;           /* 0-based SV that was detected                                          */
+    int32_t        ch;           /* channel it was handed to (lowest free one, ChanReset())                 */
+    gpsacq_peak    peak;         /* the acquisition record                                                 */
+    gpsacq_handoff start;        /* CHANNEL::Start() values, secs_since_sample = one chunk                 */
+} gpsacq_event;
+int  gpsacq_service_create(gpsacq_t *h, int num_chans /* 0 = NUM_CHANS = 12 */, int max_rounds_per_batch /* 0 = handle capacity */,
+                           gpsacq_service_t **out);
+void gpsacq_service_destroy(gpsacq_service_t *s);
+/* Consume chunks from `chunks` (n_chunks * chunk_bytes bytes) until they run out, every SV is busy, every channel
+ * is busy or max_events events were produced.  *consumed = chunks taken (feed the rest again later). */
+int  gpsacq_service_feed(gpsacq_service_t *s, const uint8_t *chunks, size_t n_chunks, size_t *consumed,
+                         gpsacq_event *events, size_t max_events, size_t *n_events);
+int  gpsacq_service_enable(gpsacq_service_t *s, int sv);        /* SearchEnable(sv), c/search.cpp:207-209          */
+int  gpsacq_service_signal_lost(gpsacq_service_t *s, int ch);   /* CHANNEL::SignalLost() frees the channel (c/channel.cpp:245-249);
+                                                                   call gpsacq_service_enable(sv) too, as :252 does */
+int  gpsacq_service_state(const gpsacq_service_t *s, uint32_t *busy_svs, uint32_t *busy_chans, int64_t *chunks_seen);
+const char *gpsacq_service_last_error(const gpsacq_service_t *s);
+
 /* Synthetic 1-bit IF capture on the GPU (what gps_sig_gen.m + cacode.m produce, generalised: several
  * satellites, Doppler, code phase, noise).  n_samples real IF samples at fs around IF fc -> packed bits,
  * LSB first, into bits_out (host, ceil(n/8) bytes) and/or d_bits_out (device); either may be NULL.

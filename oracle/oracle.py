@@ -272,3 +272,58 @@ class RefHarness:
 
     def search_code(self, sv: int, g1: int) -> int:
         return self._l.ref_search_code(sv, g1)
+
+
+# ---- consumers of the acquisition records: plain-Python restatements ----------------
+L1_HZ = 1575.42e6          # c/gps.h:22
+CPS_HZ = 1.023e6           # c/gps.h:25
+SATS_TAPS = [(2, 6), (3, 7), (4, 8), (5, 9), (1, 9), (2, 10), (1, 8), (2, 9), (3, 10), (2, 3), (3, 4), (5, 6), (6, 7),
+             (7, 8), (8, 9), (9, 10), (1, 4), (2, 5), (3, 6), (4, 7), (5, 8), (6, 9), (1, 3), (4, 6), (5, 7), (6, 8),
+             (7, 9), (8, 10), (1, 6), (2, 7), (3, 8), (4, 9)]      # Sats[], c/search.cpp:16-53 (T1, T2)
+
+
+def channel_start(sv: int, lo_shift: int, ca_shift: int, fc: float, fs: float, fft_len: int, secs: float) -> dict:
+    """CHANNEL::Start(), c/channel.cpp:134-171, as arithmetic: what it writes to the NCOs.  `secs` is
+    (Microseconds()-t_sample)/1e6 (:155).  The constants 20000/10000 of :164 are 2 and 1 code periods at the
+    receiver's FS = 10 MHz; W = ceil(fs/1000) generalises them."""
+    import math
+    lo_dop = lo_shift * fs / fft_len                                  # :147
+    ca_dop = lo_dop / L1_HZ * CPS_HZ                                  # :148
+    lo_rate = int((fc + lo_dop) / fs * math.pow(2, 32)) & 0xFFFFFFFF   # :151 (uint32_t conversion truncates)
+    ca_rate = int((CPS_HZ + ca_dop) / fs * math.pow(2, 32)) & 0xFFFFFFFF   # :152
+    ca_shift = ca_shift + int(np.rint(ca_dop * secs * fs / CPS_HZ))    # :161 nearbyint = round-half-even
+    w = math.ceil(fs / 1000.0)
+    ca_pause = int(math.fmod(2 * w - ca_shift, w))                     # :164 C's % truncates toward zero
+    t1, t2 = SATS_TAPS[sv]
+    return dict(lo_dop_hz=lo_dop, ca_dop_hz=ca_dop, lo_rate=lo_rate, ca_rate=ca_rate, ca_shift=ca_shift,
+                ca_pause=ca_pause & 0xFFFFFFFF, taps=(t1 << 4) + t2, sv=sv)      # taps: c/search.cpp:236-237
+
+
+def search_task_on_target(engine, data: bytes, num_chans: int = 12, busy=None, chan_busy: int = 0, next_sv: int = 0):
+    """SearchTask() of the receiver, c/search.cpp:214-239, ONE chunk at a time over `data`: for sv in 0..31 round
+    robin; skip Busy[sv]; stop sampling while all channels are busy (ChanReset() < 0, c/channel.cpp:396-404);
+    Sample() = the next chunk; Correlate(); snr < 25 -> continue; else Busy[sv] = true and ChanStart(ch, ...).
+    `engine` is an Oracle (or RefHarness).  Returns (events, chunks consumed, busy, chan_busy, next_sv)."""
+    busy = [False] * 32 if busy is None else list(busy)
+    cb = engine.chunk_bytes
+    n = len(data) // cb
+    pos, sv, events = 0, next_sv, []
+    while pos < n:
+        if all(busy):
+            break
+        if busy[sv]:
+            sv = (sv + 1) % 32
+            continue
+        free = [c for c in range(num_chans) if not (chan_busy >> c) & 1]
+        if not free:
+            break
+        ch = free[0]
+        p = engine.search_blocks(data[pos * cb:(pos + 1) * cb], sv_of_block=[sv])[0]
+        pos += 1
+        if not (p["snr"] < 25):
+            busy[sv] = True
+            chan_busy |= 1 << ch
+            events.append(dict(chunk_index=pos - 1, sv=sv, ch=ch, snr=float(p["snr"]), lo_shift=int(p["lo_shift"]),
+                               ca_shift=int(p["ca_shift"])))
+        sv = (sv + 1) % 32
+    return events, pos, busy, chan_busy, sv
