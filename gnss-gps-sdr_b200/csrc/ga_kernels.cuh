@@ -24,7 +24,7 @@ struct Peak { float snr, max_pwr, tot_pwr; int lo_shift, ca_shift, sv, flags, re
 
 constexpr int KTAB_MAX = 256;      // N1*RC <= 250 for the geometries below
 constexpr int K1TAB_MAX = 128;     // N1*N1 <= 100
-constexpr int NGEOM = 7;       // 3 REF geometries (N = 40000) + 4 GRID geometries (N1 = 2)
+constexpr int NGEOM = 12;      // 3 REF geometries (N = 40000) + 4 GRID embeddings (N1 = 2) + 5 exact-length GRID geometries (N1 = 1)
 __constant__ cf c_ktab[NGEOM][KTAB_MAX];
 __constant__ cf c_k1tab[NGEOM][K1TAB_MAX];
 

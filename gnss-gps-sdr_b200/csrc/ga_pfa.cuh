@@ -7,6 +7,10 @@
 #include "ga_grid.cuh"
 #include "ga_pfa.h"
 
+#ifndef PFA_PIPE_A
+#define PFA_PIPE_A 0     // measured: software-pipelined pass A is 1-4 % SLOWER (the SM already overlaps the loads across its 12-16 warps)
+#endif
+
 namespace ga {
 
 // time sample n of (block, Doppler bin d), 32-bit index arithmetic (|d|*W < 2^31 is checked at create)
@@ -76,6 +80,7 @@ __global__ void __launch_bounds__(T, MINB) pfa_cell_kernel(const cf *__restrict_
     constexpr int NWARP = T / 32;
     constexpr int NTA = cdiv(G::NA, 32), NTB = cdiv(G::NB, 32), NTC = cdiv(G::NC, 32);
     constexpr int ITA = cdiv(NTA, NWARP), ITB = cdiv(NTB, NWARP), ITC = cdiv(NTC, NWARP);
+    constexpr bool PIPE_A = PFA_PIPE_A != 0;
     constexpr int NWP = (G::RC + 1) & ~1;                            // power accumulators per butterfly, even
     constexpr uint32_t COL_SLOT = (uint32_t)((ITC * NWP + 7) & ~7);
     constexpr uint32_t TM_COLS = pow2_at_least(COL_SLOT * cdiv(NWARP, 4));
@@ -109,10 +114,29 @@ __global__ void __launch_bounds__(T, MINB) pfa_cell_kernel(const cf *__restrict_
 
         for (int k = 0; k < kblocks; k++) {
             const cf *xs = xg + ((size_t)(acq * kblocks + k) * n_dop + di) * G::W;
+            if (PIPE_A && ITA > 1) {
+                // software-pipelined pass A: the operand rows of the warp's NEXT task are in flight (registers)
+                // while the current task multiplies and runs its butterfly -- one exposed L2 round trip per
+                // pass instead of one per task
+                cf xa[G::RA], ca[G::RA], xb[G::RA], cb[G::RA];
+                const int j0 = wid * 32 + lane;
+                if (j0 < G::NA) pfa_cell_loadA<G>(j0, xs, cs, xa, ca);
 #pragma unroll 1
-            for (int it = 0; it < ITA; it++) {
-                const int j = (wid + it * NWARP) * 32 + lane;
-                if (j < G::NA) pfa_cell_passA<G>(j, xs, cs, sm);
+                for (int it = 0; it < ITA; it += 2) {
+                    const int ja = (wid + it * NWARP) * 32 + lane, jb = ja + NWARP * 32, jn = jb + NWARP * 32;
+                    if (it + 1 < ITA && jb < G::NA) pfa_cell_loadA<G>(jb, xs, cs, xb, cb);
+                    if (ja < G::NA) pfa_cell_passA_regs<G>(ja, xa, ca, sm);
+                    if (it + 1 < ITA) {
+                        if (it + 2 < ITA && jn < G::NA) pfa_cell_loadA<G>(jn, xs, cs, xa, ca);
+                        if (jb < G::NA) pfa_cell_passA_regs<G>(jb, xb, cb, sm);
+                    }
+                }
+            } else {
+#pragma unroll 1
+                for (int it = 0; it < ITA; it++) {
+                    const int j = (wid + it * NWARP) * 32 + lane;
+                    if (j < G::NA) pfa_cell_passA<G>(j, xs, cs, sm);
+                }
             }
             __syncthreads();
 #pragma unroll 1

@@ -51,6 +51,24 @@ GA_HD void pfa_cell_passA(int j, const cf *xs, const cf *cs, cf *sm)
     radix_emit<G::RA, +1>(p, [&](auto uc, cf v) { dst[decltype(uc)::value * G::template sa<0>()] = v; });
 }
 
+// the same in two steps, for software pipelining: raw operand rows into registers, then product + butterfly
+template <class G>
+GA_HD void pfa_cell_loadA(int j, const cf *xs, const cf *cs, cf (&xv)[G::RA], cf (&cv)[G::RA])
+{
+    GA_UNROLL
+    for (int a = 0; a < G::RA; a++) { xv[a] = ldg(xs + a * G::NA + j); cv[a] = ldg(cs + a * G::NA + j); }
+}
+template <class G>
+GA_HD void pfa_cell_passA_regs(int j, const cf (&xv)[G::RA], const cf (&cv)[G::RA], cf *sm)
+{
+    cf p[G::RA];
+    GA_UNROLL
+    for (int a = 0; a < G::RA; a++) p[a] = cmul(xv[a], cv[a]);
+    const int b = j / G::RC, c = j - b * G::RC;
+    cf *dst = sm + G::template sb<0>() * b + c;
+    radix_emit<G::RA, +1>(p, [&](auto uc, cf v) { dst[decltype(uc)::value * G::template sa<0>()] = v; });
+}
+
 template <class G, int DIR>
 GA_HD void pfa_passB(int j2, cf *sm)
 {

@@ -69,7 +69,16 @@ template <int F0, int F1, int F2> struct PermGeom<F0, F1, F2, 5> { typedef PGeom
 typedef PermGeom<16, 11, 31, PFA_ORDER_5456>::type P5456;    // fs = 5.456 MHz
 typedef PermGeom<24, 11, 31, PFA_ORDER_8184>::type P8184;    // fs = 8.184 MHz
 typedef PermGeom<16, 25, 7, PFA_ORDER_2800>::type P2800;      // fs = 2.8 MHz
-enum { PID_5456 = 7, PID_8184 = 8, PID_2800 = 9 };
+enum { PID_5456 = 20, PID_8184 = 21, PID_2800 = 22 };
+// GRID mode, exact-length transforms for 2/5-smooth block lengths: the same twiddled three-pass transform as the
+// embedding, but N1 = 1 and L = W (no zero padding, one code period) -- e.g. the receiver's own FS = 10 MHz
+// (c/gps.h:24), 8 / 4 MHz, and the power-of-two SDR rates 4.096 / 2.048 MHz.
+typedef Geom<1, 25, 20, 20> X10000;
+typedef Geom<1, 20, 20, 20> X8000;
+typedef Geom<1, 20, 20, 10> X4000;
+typedef Geom<1, 16, 16, 16> X4096;
+typedef Geom<1, 16, 16, 8> X2048;
+enum { XID_10000 = 7, XID_8000 = 8, XID_4000 = 9, XID_4096 = 10, XID_2048 = 11 };
 #ifndef PFA_T_5456
 #define PFA_T_5456 128      // 4 warps (a multiple of the 4 sub-partitions keeps the per-thread register budget whole)
 #endif
@@ -453,7 +462,7 @@ template <class G, int T, int MINB, bool MULTI> struct PfaOps {
         CUDA_TRY(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, h->cell_smem));
         const int want = MINB * (h->cell_smem + 2048);
         int pct = (int)((want * 100LL + 228 * 1024 - 1) / (228 * 1024));
-        if (pct > 100) pct = 100;
+        if (pct > 88) pct = 100;          // carveout steps are coarse: ask for everything when close
         CUDA_TRY(h, cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, pct));
         int per_sm = 0;
         CUDA_TRY(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, T, h->cell_smem));
@@ -500,6 +509,11 @@ template <class G, int T, int MINB, bool MULTI> struct PfaOps {
 
 #define GRID_DISPATCH(h, CALL)                                                                              \
     (h->gid >= PID_5456    ? PFA_DISPATCH(h, CALL)                                                          \
+     : h->gid == XID_10000 ? GridOps<X10000, 256, 20, XID_10000>::CALL                                      \
+     : h->gid == XID_8000  ? GridOps<X8000, 448, 20, XID_8000>::CALL                                        \
+     : h->gid == XID_4000  ? GridOps<X4000, 256, 10, XID_4000>::CALL                                        \
+     : h->gid == XID_4096  ? GridOps<X4096, 256, 16, XID_4096>::CALL                                        \
+     : h->gid == XID_2048  ? GridOps<X2048, 128, 8, XID_2048>::CALL                                         \
      : h->gid == HID_4000    ? (h->cell_nw == 7 ? GridOps<H4000, 256, 7, HID_4000>::CALL : GridOps<H4000, 256, 10, HID_4000>::CALL)      \
      : h->gid == HID_6400  ? (h->cell_nw == 14 ? GridOps<H6400, 448, 14, HID_6400>::CALL : GridOps<H6400, 448, 16, HID_6400>::CALL)    \
      : h->gid == HID_8000  ? (h->cell_nw == 14 ? GridOps<H8000, 448, 14, HID_8000>::CALL : GridOps<H8000, 448, 20, HID_8000>::CALL)    \
@@ -539,7 +553,14 @@ static int create_grid(gpsacq *h)
     h->chunk_bytes = h->block_bytes * h->kblocks;
     h->chunk_samples = h->w;
     const int pgid = pfa_gid_for(h->w, h->dmax_full);
+    const char *force_embed = getenv("GPSACQ_GRID_EMBED");
+    const bool exact_ok = !(force_embed && *force_embed && *force_embed != '0');
     if (pgid >= 0) { h->gid = pgid; h->n1 = 1; h->n2 = h->w; h->cell_nw = 0; }
+    else if (exact_ok && h->w == X10000::N2) { h->gid = XID_10000; h->n1 = 1; h->n2 = h->w; h->cell_nw = X10000::RC; }
+    else if (exact_ok && h->w == X8000::N2) { h->gid = XID_8000; h->n1 = 1; h->n2 = h->w; h->cell_nw = X8000::RC; }
+    else if (exact_ok && h->w == X4000::N2) { h->gid = XID_4000; h->n1 = 1; h->n2 = h->w; h->cell_nw = X4000::RC; }
+    else if (exact_ok && h->w == X4096::N2) { h->gid = XID_4096; h->n1 = 1; h->n2 = h->w; h->cell_nw = X4096::RC; }
+    else if (exact_ok && h->w == X2048::N2) { h->gid = XID_2048; h->n1 = 1; h->n2 = h->w; h->cell_nw = X2048::RC; }
     else if (h->w <= H4000::N2) { h->gid = HID_4000; h->n1 = 2; h->n2 = H4000::N2; h->cell_nw = h->w <= 7 * H4000::OUT_STRIDE ? 7 : 10; }
     else if (h->w <= H6400::N2) { h->gid = HID_6400; h->n1 = 2; h->n2 = H6400::N2; h->cell_nw = h->w <= 14 * H6400::OUT_STRIDE ? 14 : 16; }
     else if (h->w <= H8000::N2) { h->gid = HID_8000; h->n1 = 2; h->n2 = H8000::N2; h->cell_nw = h->w <= 14 * H8000::OUT_STRIDE ? 14 : 20; }

@@ -22,7 +22,10 @@ CASES = [
     (8.184e6, 2.046e6, 5000.0, 500.0, 1, 2, 50.0),      # configs[2]
     (2.8e6, 0.62e6, 10000.0, 250.0, 4, 2, 47.0),        # configs[3] shape (K>1, 250 Hz), reduced span for the CPU oracle
     (8.184e6, 2.046e6, 3000.0, 100.0, 3, 1, 47.0),      # configs[4] shape (100 Hz step, K>1), reduced span
-    (4.0e6, 1.0e6, 5000.0, 500.0, 2, 2, 50.0),          # W = 4000: no native transform -> zero-padded embedding path
+    (4.0e6, 1.0e6, 5000.0, 500.0, 2, 2, 50.0),          # W = 4000: exact-length twiddled transform (N1 = 1)
+    (10e6, 2.6e6, 4000.0, 500.0, 1, 1, 50.0),           # the receiver's own FS/FC (c/gps.h:23-24): W = 10000 exact
+    (2.048e6, 0.5e6, 5000.0, 500.0, 2, 2, 50.0),        # W = 2048 = 16*16*8 exact
+    (4.8e6, 1.2e6, 3000.0, 500.0, 1, 2, 50.0),          # W = 4800: no exact transform -> zero-padded embedding (L = 12800)
 ]
 
 
@@ -60,7 +63,7 @@ def test_grid_vs_oracle(ga, oracle_mod, siggen, fs, fc, max_fo, step, K, n_acq, 
         acq.close()
 
 
-@pytest.mark.parametrize("fs,fc,K", [(5.456e6, 4.092e6, 1), (8.184e6, 2.046e6, 2), (2.8e6, 0.62e6, 3)])
+@pytest.mark.parametrize("fs,fc,K", [(5.456e6, 4.092e6, 1), (8.184e6, 2.046e6, 2), (2.8e6, 0.62e6, 3), (4.096e6, 1.0e6, 2), (8.0e6, 2.0e6, 1)])
 def test_grid_native_transform_matches_embedding(ga, siggen, monkeypatch, fs, fc, K):
     """The native W-point prime-factor path (csrc/ga_pfa.cuh) and the zero-padded embedding (csrc/ga_grid.cuh)
     compute the same circular correlations: same integers, powers within float rounding."""

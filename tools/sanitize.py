@@ -1,4 +1,6 @@
-"""Small REF + GRID runs for compute-sanitizer (memcheck / racecheck / synccheck)."""
+"""Small REF + GRID runs for compute-sanitizer (memcheck / racecheck / synccheck): every kernel family once --
+REF cells (TMEM), GRID native prime-factor cells (K = 1 and K > 1 / TMEM), GRID embedding, front-end, generator."""
+import os
 import sys
 from pathlib import Path
 import numpy as np
@@ -16,3 +18,25 @@ with ga.Acquisition(2.046e6, 8.184e6, max_blocks=4) as a:
 with ga.Acquisition(4.092e6, 5.456e6, 2000.0, mode=1, doppler_step=500.0, noncoh_blocks=2, max_blocks=1) as a:
     pk = a.acquire(data[: 2 * 682])
     print("GRID", pk["lo_shift"][:4], pk["ca_shift"][:4])
+with ga.Acquisition(4.092e6, 5.456e6, 1500.0, mode=1, doppler_step=500.0, noncoh_blocks=1, max_blocks=1) as a:
+    pk = a.acquire(data[: 682])
+    print("GRID native K=1", a.info["fft_len"], pk["lo_shift"][:4], pk["ca_shift"][:4])
+with ga.Acquisition(0.62e6, 2.8e6, 1000.0, mode=1, doppler_step=250.0, noncoh_blocks=3, max_blocks=1) as a:
+    pk = a.acquire(data[: 3 * 350])
+    print("GRID native 2800 K=3", a.info["fft_len"], pk["ca_shift"][:4])
+with ga.Acquisition(2.046e6, 8.184e6, 1000.0, mode=1, doppler_step=500.0, noncoh_blocks=1, max_blocks=1, dop_first=1, dop_count=3) as a:
+    pk = a.acquire(data[: 1023])
+    print("GRID native 8184 shard", a.info["fft_len"], pk["lo_shift"][:4])
+os.environ["GPSACQ_GRID_EMBED"] = "1"
+with ga.Acquisition(4.092e6, 5.456e6, 1000.0, mode=1, doppler_step=500.0, noncoh_blocks=2, max_blocks=1) as a:
+    pk = a.acquire(data[: 2 * 682])
+    print("GRID embedding", a.info["fft_len"], pk["ca_shift"][:4])
+del os.environ["GPSACQ_GRID_EMBED"]
+with ga.Acquisition(4.092e6, 5.456e6, max_blocks=32) as a:
+    svc = ga.SearchService(a, max_rounds_per_batch=1)
+    used, ev = svc.feed(data[: 40 * 5120])
+    print("service", used, [int(e["sv"]) for e in ev])
+    svc.close()
+    iq = np.random.default_rng(1).integers(0, 256, 2 * 50000, dtype=np.uint8)
+    bits = a.iq8_to_bits(iq, 0.62e6, 2.8e6)
+    print("front-end", None if bits is None else int(bits[:4].sum()))
