@@ -126,8 +126,8 @@ struct gpsacq {
     double step;
     cf *d_wipe, *d_xg;
     float *d_code_w;
-    cudaStream_t own_stream, stream;
-    cudaEvent_t ev[4];
+    cudaStream_t own_stream, stream, copy_stream;
+    cudaEvent_t ev[4], ev_copy[8], ev_done;
     bool have_batch;
     size_t last_blocks;
     // device
@@ -183,12 +183,13 @@ template <class G, int T, int NW, int GID> struct CellKernel {
 };
 
 template <class G, int T, int NW, int GID>
-static int launch_cells_t(gpsacq *h, size_t n_blocks, const int *d_sv)
+static int launch_cells_t(gpsacq *h, size_t n_blocks, const int *d_sv, size_t off)
 {
+    // off: first workspace slot (block spectra / cell records) of this (sub-)batch
     const int n_cells = (int)(n_blocks * (size_t)h->ndop);
     const int grid = std::min(n_cells, h->cell_ctas);
     CellKernel<G, T, NW, GID>::get()<<<grid, T, h->cell_smem, h->stream>>>(
-        h->d_xd, h->d_cext, d_sv, h->d_tw, n_cells, h->ndop, h->dmax, h->w, h->d_cells);
+        h->d_xd + off * (size_t)h->n, h->d_cext, d_sv, h->d_tw, n_cells, h->ndop, h->dmax, h->w, h->d_cells + off * (size_t)h->ndop);
     CUDA_TRY(h, cudaGetLastError());
     return 0;
 }
@@ -245,18 +246,18 @@ static int setup_cells(gpsacq *h)
     }
 }
 
-static int launch_cells(gpsacq *h, size_t n_blocks, const int *d_sv)
+static int launch_cells(gpsacq *h, size_t n_blocks, const int *d_sv, size_t off = 0)
 {
     switch (h->gid) {
     case GID_4000:
-        return h->cell_nw == 7 ? launch_cells_t<G4000, CELL_T_4000, 7, GID_4000>(h, n_blocks, d_sv)
-                               : launch_cells_t<G4000, CELL_T_4000, 10, GID_4000>(h, n_blocks, d_sv);
+        return h->cell_nw == 7 ? launch_cells_t<G4000, CELL_T_4000, 7, GID_4000>(h, n_blocks, d_sv, off)
+                               : launch_cells_t<G4000, CELL_T_4000, 10, GID_4000>(h, n_blocks, d_sv, off);
     case GID_8000:
-        return h->cell_nw == 14 ? launch_cells_t<G8000, CELL_T_8000, 14, GID_8000>(h, n_blocks, d_sv)
-                                : launch_cells_t<G8000, CELL_T_8000, 20, GID_8000>(h, n_blocks, d_sv);
+        return h->cell_nw == 14 ? launch_cells_t<G8000, CELL_T_8000, 14, GID_8000>(h, n_blocks, d_sv, off)
+                                : launch_cells_t<G8000, CELL_T_8000, 20, GID_8000>(h, n_blocks, d_sv, off);
     default:
-        return h->cell_nw == 17 ? launch_cells_t<G10000, CELL_T_10000, 17, GID_10000>(h, n_blocks, d_sv)
-                                : launch_cells_t<G10000, CELL_T_10000, 20, GID_10000>(h, n_blocks, d_sv);
+        return h->cell_nw == 17 ? launch_cells_t<G10000, CELL_T_10000, 17, GID_10000>(h, n_blocks, d_sv, off)
+                                : launch_cells_t<G10000, CELL_T_10000, 20, GID_10000>(h, n_blocks, d_sv, off);
     }
 }
 
@@ -328,6 +329,9 @@ static void free_all(gpsacq *h)
     cudaFree(h->d_sv); cudaFree(h->d_wipe); cudaFree(h->d_xg); cudaFree(h->d_code_w); cudaFree(h->d_cells); cudaFree(h->d_peaks);
     cudaFreeHost(h->h_bits); cudaFreeHost(h->h_sv); cudaFreeHost(h->h_peaks);
     for (int i = 0; i < 4; i++) if (h->ev[i]) cudaEventDestroy(h->ev[i]);
+    for (int i = 0; i < 8; i++) if (h->ev_copy[i]) cudaEventDestroy(h->ev_copy[i]);
+    if (h->ev_done) cudaEventDestroy(h->ev_done);
+    if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
     if (h->own_stream) cudaStreamDestroy(h->own_stream);
 }
 
@@ -365,6 +369,9 @@ static int create_impl(gpsacq *h)
     CUDA_TRY(h, cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking));
     h->stream = h->own_stream;
     for (int i = 0; i < 4; i++) CUDA_TRY(h, cudaEventCreate(&h->ev[i]));
+    CUDA_TRY(h, cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
+    for (int i = 0; i < 8; i++) CUDA_TRY(h, cudaEventCreateWithFlags(&h->ev_copy[i], cudaEventDisableTiming));
+    CUDA_TRY(h, cudaEventCreateWithFlags(&h->ev_done, cudaEventDisableTiming));
 
     const size_t n = (size_t)h->n, cap = (size_t)h->cap;
     CUDA_TRY(h, cudaMalloc(&h->d_tw, n * sizeof(cf)));
@@ -731,6 +738,24 @@ int gpsacq_synchronize(gpsacq_t *h)
     return GPSACQ_OK;
 }
 
+// one (sub-)batch on the handle's stream; workspace slots [off, off + n_blocks)
+// (`timed`: record the stage events -- the last slice of a sliced host batch, see gpsacq_stage_times)
+static int search_device_impl(gpsacq *h, const uint8_t *d_bits, size_t n_blocks, const int32_t *d_sv, gpsacq_peak *d_out, size_t off,
+                              bool last)
+{
+    if (last) CUDA_TRY(h, cudaEventRecord(h->ev[0], h->stream));
+    int rc = launch_fwd(h, 0, n_blocks, d_bits, h->d_xd + off * (size_t)h->n);
+    if (rc) return rc;
+    if (last) CUDA_TRY(h, cudaEventRecord(h->ev[1], h->stream));
+    rc = launch_cells(h, n_blocks, d_sv, off);
+    if (rc) return rc;
+    if (last) CUDA_TRY(h, cudaEventRecord(h->ev[2], h->stream));
+    best_kernel<<<(unsigned)((n_blocks + 3) / 4), 128, 0, h->stream>>>(h->d_cells + off * (size_t)h->ndop, d_sv, (int)n_blocks, h->ndop, h->dmax, h->w, (Peak *)d_out);
+    CUDA_TRY(h, cudaGetLastError());
+    if (last) CUDA_TRY(h, cudaEventRecord(h->ev[3], h->stream));
+    return GPSACQ_OK;
+}
+
 int gpsacq_search_blocks_device(gpsacq_t *h, const uint8_t *d_bits, size_t n_blocks, const int32_t *d_sv, gpsacq_peak *d_out)
 {
     if (!h || !d_bits || !d_out) return GPSACQ_EINVAL;
@@ -738,38 +763,45 @@ int gpsacq_search_blocks_device(gpsacq_t *h, const uint8_t *d_bits, size_t n_blo
     if (n_blocks == 0) return GPSACQ_OK;
     if (n_blocks > (size_t)h->cap) { h->err = "n_blocks exceeds max_blocks"; return GPSACQ_EINVAL; }
     CUDA_TRY(h, cudaSetDevice(h->device));
-    CUDA_TRY(h, cudaEventRecord(h->ev[0], h->stream));
-    int rc = launch_fwd(h, 0, n_blocks, d_bits, h->d_xd);
+    const int rc = search_device_impl(h, d_bits, n_blocks, d_sv, d_out, 0, true);
     if (rc) return rc;
-    CUDA_TRY(h, cudaEventRecord(h->ev[1], h->stream));
-    rc = launch_cells(h, n_blocks, d_sv);
-    if (rc) return rc;
-    CUDA_TRY(h, cudaEventRecord(h->ev[2], h->stream));
-    best_kernel<<<(unsigned)((n_blocks + 3) / 4), 128, 0, h->stream>>>(h->d_cells, d_sv, (int)n_blocks, h->ndop, h->dmax, h->w, (Peak *)d_out);
-    CUDA_TRY(h, cudaGetLastError());
-    CUDA_TRY(h, cudaEventRecord(h->ev[3], h->stream));
     h->have_batch = true;
     h->last_blocks = n_blocks;
     return GPSACQ_OK;
 }
 
+// Host-buffer search.  A batch is cut into up to 4 slices: while the GPU searches slice i the host stages slice
+// i+1 into pinned memory and the copy engine moves it (copy stream + events), so that only the first slice's
+// transfer is exposed.  Results come back with one device->host copy per batch.
 int gpsacq_search_blocks(gpsacq_t *h, const uint8_t *bits, size_t n_blocks, const int32_t *sv_of_block, gpsacq_peak *out)
 {
     if (!h || (!bits && n_blocks) || (!out && n_blocks)) return GPSACQ_EINVAL;
     if (h->mode != GPSACQ_MODE_REF) { h->err = "gpsacq_search_blocks needs a GPSACQ_MODE_REF handle"; return GPSACQ_EINVAL; }
     CUDA_TRY(h, cudaSetDevice(h->device));
+    const size_t cb = (size_t)h->chunk_bytes;
     for (size_t done = 0; done < n_blocks;) {
         const size_t nb = std::min((size_t)h->cap, n_blocks - done);
-        memcpy(h->h_bits, bits + done * (size_t)h->chunk_bytes, nb * (size_t)h->chunk_bytes);
         for (size_t b = 0; b < nb; b++) {
             const int sv = sv_of_block ? sv_of_block[done + b] : (int)((done + b) % GPSACQ_NUM_SATS);
             if (sv < 0 || sv >= GPSACQ_NUM_SATS) { h->err = "sv_of_block entry out of range 0..31"; return GPSACQ_EINVAL; }
             h->h_sv[b] = sv;
         }
-        CUDA_TRY(h, cudaMemcpyAsync(h->d_bits, h->h_bits, nb * (size_t)h->chunk_bytes, cudaMemcpyHostToDevice, h->stream));
-        CUDA_TRY(h, cudaMemcpyAsync(h->d_sv, h->h_sv, nb * sizeof(int), cudaMemcpyHostToDevice, h->stream));
-        int rc = gpsacq_search_blocks_device(h, h->d_bits, nb, h->d_sv, (gpsacq_peak *)h->d_peaks);
-        if (rc) return rc;
+        const size_t n_slices = nb >= 256 ? 4 : nb >= 64 ? 2 : 1;
+        // the previous batch's kernels may still read d_bits / d_sv: the copy stream waits for them
+        CUDA_TRY(h, cudaEventRecord(h->ev_done, h->stream));
+        CUDA_TRY(h, cudaStreamWaitEvent(h->copy_stream, h->ev_done, 0));
+        CUDA_TRY(h, cudaMemcpyAsync(h->d_sv, h->h_sv, nb * sizeof(int), cudaMemcpyHostToDevice, h->copy_stream));
+        for (size_t i = 0; i < n_slices; i++) {
+            const size_t lo = nb * i / n_slices, n = nb * (i + 1) / n_slices - lo;
+            memcpy(h->h_bits + lo * cb, bits + (done + lo) * cb, n * cb);
+            CUDA_TRY(h, cudaMemcpyAsync(h->d_bits + lo * cb, h->h_bits + lo * cb, n * cb, cudaMemcpyHostToDevice, h->copy_stream));
+            CUDA_TRY(h, cudaEventRecord(h->ev_copy[i], h->copy_stream));
+            CUDA_TRY(h, cudaStreamWaitEvent(h->stream, h->ev_copy[i], 0));
+            const int rc = search_device_impl(h, h->d_bits + lo * cb, n, h->d_sv + lo, (gpsacq_peak *)(h->d_peaks + lo), lo, i + 1 == n_slices);
+            if (rc) return rc;
+        }
+        h->have_batch = true;
+        h->last_blocks = nb;
         CUDA_TRY(h, cudaMemcpyAsync(h->h_peaks, h->d_peaks, nb * sizeof(Peak), cudaMemcpyDeviceToHost, h->stream));
         CUDA_TRY(h, cudaStreamSynchronize(h->stream));
         memcpy(out + done, h->h_peaks, nb * sizeof(Peak));

@@ -263,7 +263,8 @@ int  gpsacq_synth_capture(int device, double fs, double fc, const gpsacq_sat *sa
 /* Elapsed milliseconds of the stages of the most recent batch, measured with CUDA
  * events on the launching stream: [0] unpack+mix+forward FFT kernel, [1] cell kernel
  * (conj-multiply + backward FFT + peak), [2] best-over-Doppler kernel, [3] whole batch.
- * Synchronises the stream. */
+ * (gpsacq_search_blocks() cuts large host batches into slices to overlap transfers with compute: the times
+ * are then those of the LAST slice.)  Synchronises the stream. */
 int  gpsacq_stage_times(gpsacq_t *h, float ms[4]);
 
 /* ---- parity probes (copy device state to host; synchronise) -------------------- */
