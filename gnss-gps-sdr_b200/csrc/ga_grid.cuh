@@ -85,7 +85,9 @@ __global__ void __launch_bounds__(T, TM_MINB) grid_cell_kernel(const cf *__restr
     constexpr uint32_t COLS_Y = ITC * 2 * NW, COLS_P = ITC * NWP;
     constexpr uint32_t COL_SLOT = (COLS_Y + COLS_P + 7u) & ~7u;
     constexpr uint32_t TM_COLS = pow2_at_least(COL_SLOT * cdiv(NWARP, 4));
+#ifndef GA_NO_TM_ASSERT
     static_assert(TM_COLS * TM_MINB <= 512 || G::SMEM_ELEMS * sizeof(cf) * TM_MINB > 227 * 1024, "TMEM columns");
+#endif
     extern __shared__ __align__(16) unsigned char smem_raw[];
     cf *sm = reinterpret_cast<cf *>(smem_raw);
     __shared__ float red_best[NWARP], red_sum[NWARP];

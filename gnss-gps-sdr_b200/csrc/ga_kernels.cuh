@@ -285,6 +285,13 @@ constexpr uint32_t pow2_at_least(uint32_t x, uint32_t p = 32) { return p >= x ? 
 #define TM_MINB 2     // CTAs per SM the TMEM kernel is sized for
 #endif
 
+// task loops of cell_kernel_tm: fully unrolled (one task per warp in the default 448-thread shape); CTA shapes with
+// several tasks per warp (experiments) must not unroll, or the compiler hoists every task's loads and spills
+#ifdef GA_IT_UNROLL1
+#define GA_IT_PRAGMA _Pragma("unroll 1")
+#else
+#define GA_IT_PRAGMA _Pragma("unroll")
+#endif
 template <class G, int T, int NW, int GID>
 __global__ void __launch_bounds__(T, TM_MINB) cell_kernel_tm(const cf *__restrict__ xd, const cf *__restrict__ cext,
                                                        const int *__restrict__ sv_of_block, const cf *__restrict__ tw,
@@ -336,20 +343,20 @@ __global__ void __launch_bounds__(T, TM_MINB) cell_kernel_tm(const cf *__restric
             cell_sub_offsets<G>(s, dop, sp, eoff);
             const cf *xs = xb + (size_t)s * G::N2;
             const cf *cs = cb + (size_t)sp * (2 * G::N2) + eoff;
-#pragma unroll
+GA_IT_PRAGMA
             for (int it = 0; it < ITA; it++) {
                 const int j = (vw + it * NWARP) * 32 + lane;
                 if (j < G::NA) cell_passA<G>(j, s, xs, cs, tw, sm);
             }
             __syncthreads();
-#pragma unroll
+GA_IT_PRAGMA
             for (int it = 0; it < ITB; it++) {
                 const int j = (vw + it * NWARP) * 32 + lane;
                 if (j < G::NB) passB<G, +1>(j, s, tw, sm);
             }
             __syncthreads();
             const cf *ks = c_ktab[GID] + s * G::RC;
-#pragma unroll
+GA_IT_PRAGMA
             for (int it = 0; it < ITC; it++) {
                 const int task = vw + it * NWARP;
                 if (task < NTC) {          // warp-uniform

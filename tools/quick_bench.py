@@ -17,6 +17,6 @@ ts = []
 for i in range(10):
     acq.search_blocks(bits); ts.append(acq.stage_times())
 c = np.median([t["cells_ms"] for t in ts]); f = np.median([t["fwd_ms"] for t in ts]); tot = np.median([t["total_ms"] for t in ts])
-n = 512 * acq.n_doppler
+n = 512 * acq.n_doppler // 4          # the host-buffer call is cut into 4 slices; stage_times() are those of the last slice (128 chunks)
 print("%s fs=%.3g: cells %.3f ms -> %.3f Mcorr/s (%.1f%% of 6489.9 GB/s) fwd %.3f total %.3f  checksum %.6e" % (
     os.environ.get("GPSACQ_LIB", "default"), fs, c, n / c / 1e3, n / c * 1e3 * 640016 / 6489.9e9 * 100, f, tot, float(pk["snr"].astype(np.float64).sum())))
