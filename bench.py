@@ -63,7 +63,7 @@ def workload_config(n_gpus: int):
     return {"workload": "C1-REF: synthetic 1-bit IF fs=5.456MHz if=4.092MHz, 32 PRN x 73 Doppler bins "
                         "(+-5 kHz @ 136.4 Hz), N=40000 coherent (7.33 ms), 16 runs (512 chunks) per GPU per step",
             "correlations_per_step_per_gpu": RUNS_PER_STEP * 32 * 73,
-            "sharding": f"runs of the stream split over {n_gpus} GPU(s); NCCL all-gather of peak records"
+            "sharding": f"runs of the stream split over {n_gpus} GPU(s); NCCL all-gather of peak records, overlapped with the next step (double-buffered records)"
                         if n_gpus > 1 else "single GPU",
             "l2_policy": "inputs larger than L2: each step's cell-kernel operands are 164 MB of block spectra "
                          "+ 20 MB of replica spectra (> 126 MB L2); 4 distinct input batches are cycled"}
@@ -230,17 +230,28 @@ def run_engine(args, rank, world, local_rank):
     corr_per_step = nb * ndop
     d_bits = [torch.from_numpy(b).to(dev) for b in batches]
     h_bits = [torch.from_numpy(b).pin_memory() for b in batches]
-    d_out = torch.zeros(nb * 32, dtype=torch.uint8, device=dev)
-    d_all = torch.zeros(world * nb * 32, dtype=torch.uint8, device=dev) if world > 1 else None
+    # records double-buffered: the NCCL all-gather of step i runs (on NCCL's stream) while step i+1 computes
+    d_outs = [torch.zeros(nb * 32, dtype=torch.uint8, device=dev) for _ in range(2)]
+    d_alls = [torch.zeros(world * nb * 32, dtype=torch.uint8, device=dev) for _ in range(2)] if world > 1 else None
+    works = [None, None]
     # a non-default stream: libgpsacq launches on it and the CUDA events below are recorded on it
     stream = torch.cuda.Stream(device=dev)
     torch.cuda.set_stream(stream)
     acq.set_stream(stream.cuda_stream)
 
     def step_device(i):
-        acq.search_blocks_device(d_bits[i % N_BATCHES].data_ptr(), nb, None, d_out.data_ptr())
+        k = i & 1
+        if works[k] is not None:
+            works[k].wait()                    # the gather that last used this buffer pair (two steps ago) is done
+        acq.search_blocks_device(d_bits[i % N_BATCHES].data_ptr(), nb, None, d_outs[k].data_ptr())
         if world > 1:
-            dist.all_gather_into_tensor(d_all, d_out)
+            works[k] = dist.all_gather_into_tensor(d_alls[k], d_outs[k], async_op=True)
+
+    def drain():
+        for k in range(2):
+            if works[k] is not None:
+                works[k].wait()                # makes the current stream wait for the collective
+                works[k] = None
 
     def barrier():
         if world > 1:
@@ -250,6 +261,7 @@ def run_engine(args, rank, world, local_rank):
     # ---- device-resident timing ------------------------------------------------------------------
     for i in range(args.warmup):
         step_device(i)
+    drain()
     barrier()
     sampler = ClockSampler(local_rank)
     sampler.start()
@@ -258,6 +270,7 @@ def run_engine(args, rank, world, local_rank):
     e0.record(stream)
     for i in range(args.steps):
         step_device(i)
+    drain()
     e1.record(stream)
     barrier()
     total_ms = e0.elapsed_time(e1)
@@ -265,6 +278,7 @@ def run_engine(args, rank, world, local_rank):
     for i in range(min(args.steps, 8)):
         step_device(i)
         cell_ms.append(acq.stage_times()["cells_ms"])
+    drain()
     barrier()
     clocks = sampler.finish()
     stage = acq.stage_times()
