@@ -275,6 +275,9 @@ class RefHarness:
 
 
 # ---- consumers of the acquisition records: plain-Python restatements ----------------
+# PARITY UNPINNED for these two: c/channel.cpp and c/search.cpp need the receiver's FPGA/SPI layer and cannot be built
+# or run here; the restatements follow the cited lines, and the per-chunk Sample()+Correlate() they call is the pinned
+# oracle above.
 L1_HZ = 1575.42e6          # c/gps.h:22
 CPS_HZ = 1.023e6           # c/gps.h:25
 SATS_TAPS = [(2, 6), (3, 7), (4, 8), (5, 9), (1, 9), (2, 10), (1, 8), (2, 9), (3, 10), (2, 3), (3, 4), (5, 6), (6, 7),
