@@ -335,6 +335,31 @@ static void free_all(gpsacq *h)
     if (h->own_stream) cudaStreamDestroy(h->own_stream);
 }
 
+// device, streams and events of a handle (both modes).  Fails loudly when there is no usable sm_100 device:
+// the library has no CPU path.
+static int open_device(gpsacq *h)
+{
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0) {
+        h->err = std::string("no CUDA device available (") + cudaGetErrorString(e) + "); libgpsacq has no CPU fallback";
+        return GPSACQ_ECUDA;
+    }
+    if (h->cfg.device >= 0) { CUDA_TRY(h, cudaSetDevice(h->cfg.device)); }
+    CUDA_TRY(h, cudaGetDevice(&h->device));
+    cudaDeviceProp prop;
+    CUDA_TRY(h, cudaGetDeviceProperties(&prop, h->device));
+    if (prop.major < 10) { h->err = "libgpsacq is built for sm_100a (B200) only"; return GPSACQ_ECUDA; }
+    h->sm_count = prop.multiProcessorCount;
+    CUDA_TRY(h, cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking));
+    h->stream = h->own_stream;
+    for (int i = 0; i < 4; i++) CUDA_TRY(h, cudaEventCreate(&h->ev[i]));
+    CUDA_TRY(h, cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
+    for (int i = 0; i < 8; i++) CUDA_TRY(h, cudaEventCreateWithFlags(&h->ev_copy[i], cudaEventDisableTiming));
+    CUDA_TRY(h, cudaEventCreateWithFlags(&h->ev_done, cudaEventDisableTiming));
+    return GPSACQ_OK;
+}
+
 static int create_impl(gpsacq *h)
 {
     const gpsacq_cfg &c = h->cfg;
@@ -353,25 +378,7 @@ static int create_impl(gpsacq *h)
     else { h->err = "sampling rates above 10 MHz (W > 10000) are not supported yet"; return GPSACQ_EINVAL; }
     if (h->dmax >= h->n2) { h->err = "max_fo too large for this fft_len"; return GPSACQ_EINVAL; }
 
-    int ndev = 0;
-    cudaError_t e = cudaGetDeviceCount(&ndev);
-    if (e != cudaSuccess || ndev == 0) {
-        h->err = std::string("no CUDA device available (") + cudaGetErrorString(e) + "); libgpsacq has no CPU fallback";
-        return GPSACQ_ECUDA;
-    }
-    if (c.device >= 0) { CUDA_TRY(h, cudaSetDevice(c.device)); }
-    CUDA_TRY(h, cudaGetDevice(&h->device));
-    cudaDeviceProp prop;
-    CUDA_TRY(h, cudaGetDeviceProperties(&prop, h->device));
-    if (prop.major < 10) { h->err = "libgpsacq is built for sm_100a (B200) only"; return GPSACQ_ECUDA; }
-    h->sm_count = prop.multiProcessorCount;
-
-    CUDA_TRY(h, cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking));
-    h->stream = h->own_stream;
-    for (int i = 0; i < 4; i++) CUDA_TRY(h, cudaEventCreate(&h->ev[i]));
-    CUDA_TRY(h, cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
-    for (int i = 0; i < 8; i++) CUDA_TRY(h, cudaEventCreateWithFlags(&h->ev_copy[i], cudaEventDisableTiming));
-    CUDA_TRY(h, cudaEventCreateWithFlags(&h->ev_done, cudaEventDisableTiming));
+    { const int rc_dev = open_device(h); if (rc_dev) return rc_dev; }
 
     const size_t n = (size_t)h->n, cap = (size_t)h->cap;
     CUDA_TRY(h, cudaMalloc(&h->d_tw, n * sizeof(cf)));
@@ -575,21 +582,7 @@ static int create_grid(gpsacq *h)
     else { h->err = "sampling rates above 10 MHz are not supported yet"; return GPSACQ_EINVAL; }
     h->n = h->n1 * h->n2;                                      // L
 
-    int ndev = 0;
-    cudaError_t e = cudaGetDeviceCount(&ndev);
-    if (e != cudaSuccess || ndev == 0) {
-        h->err = std::string("no CUDA device available (") + cudaGetErrorString(e) + "); libgpsacq has no CPU fallback";
-        return GPSACQ_ECUDA;
-    }
-    if (c.device >= 0) { CUDA_TRY(h, cudaSetDevice(c.device)); }
-    CUDA_TRY(h, cudaGetDevice(&h->device));
-    cudaDeviceProp prop;
-    CUDA_TRY(h, cudaGetDeviceProperties(&prop, h->device));
-    if (prop.major < 10) { h->err = "libgpsacq is built for sm_100a (B200) only"; return GPSACQ_ECUDA; }
-    h->sm_count = prop.multiProcessorCount;
-    CUDA_TRY(h, cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking));
-    h->stream = h->own_stream;
-    for (int i = 0; i < 4; i++) CUDA_TRY(h, cudaEventCreate(&h->ev[i]));
+    { const int rc_dev = open_device(h); if (rc_dev) return rc_dev; }
 
     // batch capacity: keep the block spectra of one batch under ~3 GB
     const size_t per_acq = (size_t)h->kblocks * h->ndop * h->n * sizeof(cf);
