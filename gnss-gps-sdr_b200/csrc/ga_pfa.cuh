@@ -56,6 +56,22 @@ __global__ void __launch_bounds__(T) pfa_fwd_kernel(const unsigned char *__restr
     for (int j = threadIdx.x; j < F::NC; j += T) pfa_fwd_passC_store<F, MODE == 0>(j, sm, dst);
 }
 
+// rotated copies of the 32 replica spectra: out[(q - q_min)*32 + prn][pos(a,b,c)] = C_prn[k(a,b,c) - q]
+template <class G>
+__global__ void pfa_rotate_replicas_kernel(const cf *__restrict__ crep, int q_min, cf *__restrict__ out)
+{
+    const int q = q_min + (int)blockIdx.y, prn = blockIdx.z;
+    const PfaRot r = pfa_rotation<G>(-q);
+    const cf *src = crep + (size_t)prn * G::W;
+    cf *dst = out + ((size_t)blockIdx.y * 32 + prn) * G::W;
+    for (int m = blockIdx.x * blockDim.x + threadIdx.x; m < G::W; m += gridDim.x * blockDim.x) {
+        int a = m / G::NA;
+        const int j = m - a * G::NA;
+        a += r.da; if (a >= G::RA) a -= G::RA;
+        dst[m] = src[a * G::NA + pfa_rot_col<G>(j, r)];
+    }
+}
+
 // slow path of the K = 1 statistics: redo one pass-C butterfly (its inputs are still in shared memory)
 // comparing lags on every tie.  Kept out of line: it is practically never executed.
 template <class G>
@@ -74,7 +90,8 @@ __device__ __noinline__ void pfa_passC_exact(int jc, const cf *sm, int t0, float
 // (tcgen05.ld/st, as in cell_kernel_tm) and the statistics are taken on the sum.
 template <class G, int T, int MINB, bool MULTI>
 __global__ void __launch_bounds__(T, MINB) pfa_cell_kernel(const cf *__restrict__ xg, const cf *__restrict__ crep,
-                                                           int n_cells, int n_dop, int kblocks, CellStat *__restrict__ cells)
+                                                           int n_cells, int n_dop, int dmax, int n_base, int q_min, int kblocks,
+                                                           CellStat *__restrict__ cells)
 {
     static_assert(T % 32 == 0, "whole warps only");
     constexpr int NWARP = T / 32;
@@ -111,9 +128,20 @@ __global__ void __launch_bounds__(T, MINB) pfa_cell_kernel(const cf *__restrict_
         const cf *cs = crep + (size_t)prn * G::W;
         float best = 0.0f, sum = 0.0f;
         int besti = 0;
+        // n_base = R > 0: only the bins 0..R-1 of each block were transformed (Doppler bins R apart are one DFT bin
+        // apart): bin d = r + R*q reads block spectrum r and the replica spectrum rotated by -q (ga_pfa.h);
+        // n_base = 0: one block spectrum per bin, unrotated replicas
+        int xsel = di, xstride = n_dop;
+        if (n_base > 0) {
+            const int d = di - dmax;
+            int rr = d % n_base;
+            if (rr < 0) rr += n_base;
+            xsel = rr; xstride = n_base;
+            cs = crep + ((size_t)((d - rr) / n_base - q_min) * 32 + prn) * G::W;
+        }
 
         for (int k = 0; k < kblocks; k++) {
-            const cf *xs = xg + ((size_t)(acq * kblocks + k) * n_dop + di) * G::W;
+            const cf *xs = xg + ((size_t)(acq * kblocks + k) * xstride + xsel) * G::W;
             if (PIPE_A && ITA > 1) {
                 // software-pipelined pass A: the operand rows of the warp's NEXT task are in flight (registers)
                 // while the current task multiplies and runs its butterfly -- one exposed L2 round trip per

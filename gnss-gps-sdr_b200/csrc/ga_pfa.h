@@ -34,8 +34,39 @@ struct PGeom : Geom<1, RA_, RB_, RC_> {
     static constexpr int EC = (W / RC_) * cx_inv_mod((W / RC_) % RC_, RC_);
     // Good's map strides: k = (a*KA + b*KB + c*KC) mod W
     static constexpr int KA = W / RA_, KB = W / RB_, KC = W / RC_;
+    // spectral index k -> k + 1 moves (a,b,c) by (IA,IB,IC) per axis, cyclically:  a = (k mod RA) * KA^-1 mod RA, ...
+    static constexpr int IA = cx_inv_mod(KA % RA_, RA_), IB = cx_inv_mod(KB % RB_, RB_), IC = cx_inv_mod(KC % RC_, RC_);
     typedef PGeom<RB_, RC_, RA_> Fwd;     // the forward transform's factorisation (see header)
 };
+
+// Rotation of a spectrum stored in (a,b,c)-linear order by q spectral bins (S'[k] = S[k+q]): every axis shifts
+// cyclically.  Used to share forward transforms between Doppler bins that are a whole DFT bin apart:
+// exp(-j2pi(d + R)n/M) = exp(-j2pi d n/M) * exp(-j2pi n/W) when M = R*W, i.e. X_{d+R}[k] = X_d[k+1].  With
+// d = r + R*q:  conj(X_d[k]) C[k] = conj(X_r[k+q]) C[k]  is a circular shift (by q) of  conj(X_r[k]) C[k-q],  and a
+// circular shift of the product spectrum only puts a unit-modulus ramp on the lags: |y|^2 is unchanged.  So the
+// cell multiplies the UNROTATED block spectrum X_r with a replica spectrum rotated by -q, and the rotated replicas
+// are made once at create time (pfa_rotate_replicas_kernel) -- the hot loop pays nothing.
+struct PfaRot { int da, db, dc; };
+template <class G>
+GA_HD PfaRot pfa_rotation(int q)
+{
+    PfaRot r;
+    int qa = q % G::RA, qb = q % G::RB, qc = q % G::RC;
+    if (qa < 0) qa += G::RA;
+    if (qb < 0) qb += G::RB;
+    if (qc < 0) qc += G::RC;
+    r.da = (qa * G::IA) % G::RA; r.db = (qb * G::IB) % G::RB; r.dc = (qc * G::IC) % G::RC;
+    return r;
+}
+// position (within a row of NA) that thread j = b*RC + c reads the rotated operand from
+template <class G>
+GA_HD int pfa_rot_col(int j, const PfaRot &r)
+{
+    int b = j / G::RC, c = j - b * G::RC;
+    b += r.db; if (b >= G::RB) b -= G::RB;
+    c += r.dc; if (c >= G::RC) c -= G::RC;
+    return b * G::RC + c;
+}
 
 // ---- passes, in place in shared memory; DIR = +1 backward, -1 forward ------------------------
 // pass A of a cell: thread j = b*RC + c of NA.  xs = conj(X) of the block (W values, (a,b,c) order),

@@ -122,6 +122,9 @@ struct gpsacq {
     int gid, n, n1, n2, w, dmax, ndop, chunk_bytes, chunk_samples, cap, device, sm_count;
     int cell_ctas, cell_threads, cell_smem, cell_nw;
     int mode, kblocks, wipe_m, block_bytes, cap_acq;
+    int q_min, n_q;                    // GRID, native path: replica spectra are stored rotated by -q for q_min <= q < q_min + n_q
+    cf *d_crot;
+    int n_base;                        // GRID, native path: R = 1000/step base spectra per block shared by all bins (0 = one per bin)
     int dmax_full, dop_first;          // GRID shard: h->dmax is dmax_full - dop_first, so that bin = index - h->dmax is absolute
     double step;
     cf *d_wipe, *d_xg;
@@ -326,7 +329,7 @@ static void free_all(gpsacq *h)
     if (!h) return;
     cudaFree(h->d_tw); cudaFree(h->d_lo); cudaFree(h->d_chip_idx); cudaFree(h->d_blend_a); cudaFree(h->d_blend_b);
     cudaFree(h->d_repl_time); cudaFree(h->d_cext); cudaFree(h->d_xd); cudaFree(h->d_nat); cudaFree(h->d_bits);
-    cudaFree(h->d_sv); cudaFree(h->d_wipe); cudaFree(h->d_xg); cudaFree(h->d_code_w); cudaFree(h->d_cells); cudaFree(h->d_peaks);
+    cudaFree(h->d_crot); cudaFree(h->d_sv); cudaFree(h->d_wipe); cudaFree(h->d_xg); cudaFree(h->d_code_w); cudaFree(h->d_cells); cudaFree(h->d_peaks);
     cudaFreeHost(h->h_bits); cudaFreeHost(h->h_sv); cudaFreeHost(h->h_peaks);
     for (int i = 0; i < 4; i++) if (h->ev[i]) cudaEventDestroy(h->ev[i]);
     for (int i = 0; i < 8; i++) if (h->ev_copy[i]) cudaEventDestroy(h->ev_copy[i]);
@@ -464,6 +467,7 @@ template <class H, int T, int NW, int HID> struct GridOps {
         return 0;
     }
     static int replicas(gpsacq *h) { return launch_fwd_t<H, 1, HID>(h, 32, nullptr, h->d_cext); }
+    static int rotate(gpsacq *) { return 0; }
     static int consts(gpsacq *h) { return upload_const_t<H, HID>(h); }
 };
 
@@ -492,8 +496,11 @@ template <class G, int T, int MINB, bool MULTI> struct PfaOps {
     static int fwd_blocks(gpsacq *h, size_t n_blocks, const unsigned char *d_bits)
     {
         typedef typename G::Fwd F;
-        pfa_fwd_kernel<G, FWD_T, 0><<<(unsigned)(n_blocks * h->ndop), FWD_T, F::SMEM_ELEMS * sizeof(cf), h->stream>>>(
-            d_bits, h->block_bytes, h->d_lo, h->d_wipe, h->ndop, h->dmax, h->wipe_m, nullptr, h->d_xg);
+        // one transform per (block, Doppler bin) -- or, when bins repeat every n_base = R bins up to a spectral
+        // rotation, only for the bins 0..R-1 (pfa_cell_kernel rotates)
+        const int items = h->n_base > 0 ? h->n_base : h->ndop, item_dmax = h->n_base > 0 ? 0 : h->dmax;
+        pfa_fwd_kernel<G, FWD_T, 0><<<(unsigned)(n_blocks * items), FWD_T, F::SMEM_ELEMS * sizeof(cf), h->stream>>>(
+            d_bits, h->block_bytes, h->d_lo, h->d_wipe, items, item_dmax, h->wipe_m, nullptr, h->d_xg);
         CUDA_TRY(h, cudaGetLastError());
         return 0;
     }
@@ -501,7 +508,8 @@ template <class G, int T, int MINB, bool MULTI> struct PfaOps {
     {
         const int n_cells = (int)(n_acq * 32 * (size_t)h->ndop);
         const int grid = std::min(n_cells, h->cell_ctas);
-        pfa_cell_kernel<G, T, MINB, MULTI><<<grid, T, h->cell_smem, h->stream>>>(h->d_xg, h->d_cext, n_cells, h->ndop, h->kblocks, h->d_cells);
+        pfa_cell_kernel<G, T, MINB, MULTI><<<grid, T, h->cell_smem, h->stream>>>(h->d_xg, h->n_base > 0 ? h->d_crot : h->d_cext, n_cells, h->ndop,
+                                                                                 h->dmax, h->n_base, h->q_min, h->kblocks, h->d_cells);
         CUDA_TRY(h, cudaGetLastError());
         return 0;
     }
@@ -514,6 +522,12 @@ template <class G, int T, int MINB, bool MULTI> struct PfaOps {
         return 0;
     }
     static int consts(gpsacq *) { return 0; }            // no twiddle tables: Good-Thomas
+    static int rotate(gpsacq *h)                         // the replica spectra rotated by -q, q_min <= q < q_min + n_q
+    {
+        pfa_rotate_replicas_kernel<G><<<dim3(8, (unsigned)h->n_q, 32), 256, 0, h->stream>>>(h->d_cext, h->q_min, h->d_crot);
+        CUDA_TRY(h, cudaGetLastError());
+        return 0;
+    }
 };
 
 #define PFA_DISPATCH(h, CALL)                                                                               \
@@ -584,8 +598,16 @@ static int create_grid(gpsacq *h)
 
     { const int rc_dev = open_device(h); if (rc_dev) return rc_dev; }
 
+    // Doppler bins R = 1000/step apart differ by exactly one DFT bin of the 1 ms block (M = R*W): the native path
+    // transforms only the bins 0..R-1 of each block and rotates (GPSACQ_GRID_NOSHARE=1 turns this off, for A/B runs)
+    h->n_base = 0;
+    {
+        const char *ns = getenv("GPSACQ_GRID_NOSHARE");
+        const int r = h->w > 0 ? h->wipe_m / h->w : 0;
+        if (h->gid >= PID_5456 && !(ns && *ns && *ns != '0') && r >= 1 && (long long)r * h->w == h->wipe_m && r < h->ndop) h->n_base = r;
+    }
     // batch capacity: keep the block spectra of one batch under ~3 GB
-    const size_t per_acq = (size_t)h->kblocks * h->ndop * h->n * sizeof(cf);
+    const size_t per_acq = (size_t)h->kblocks * (h->n_base > 0 ? h->n_base : h->ndop) * h->n * sizeof(cf);
     size_t cap = (size_t)3 << 30;
     cap = std::max<size_t>(1, cap / per_acq);
     if (c.max_blocks > 0) cap = std::min<size_t>(cap, (size_t)c.max_blocks);
@@ -639,6 +661,16 @@ static int create_grid(gpsacq *h)
     }
     rc = GRID_DISPATCH(h, replicas(h));
     if (rc) return rc;
+    if (h->n_base > 0) {
+        // bins of this handle: d in [-dmax, -dmax + ndop); q = floor(d / R)
+        const int d_lo = -h->dmax, d_hi = -h->dmax + h->ndop - 1;
+        auto fdiv = [](int a, int b) { int q = a / b; return (a % b != 0 && (a < 0)) ? q - 1 : q; };
+        h->q_min = fdiv(d_lo, h->n_base);
+        h->n_q = fdiv(d_hi, h->n_base) - h->q_min + 1;
+        CUDA_TRY(h, cudaMalloc(&h->d_crot, (size_t)h->n_q * 32 * W * sizeof(cf)));
+        rc = GRID_DISPATCH(h, rotate(h));
+        if (rc) return rc;
+    }
     CUDA_TRY(h, cudaStreamSynchronize(h->stream));
     return 0;
 }

@@ -113,8 +113,17 @@ static void emu_pfa_fwd_t(const cf *x, int conj, cf *out)
 }
 
 template <class G>
-static void emu_pfa_cell_t(const cf *xs, const cf *cs, cf *y, float *best, int *besti, float *sum, int *n_slow)
+static void emu_pfa_cell_t(const cf *xs, const cf *cs_in, int q, cf *y, float *best, int *besti, float *sum, int *n_slow)
 {
+    // what pfa_rotate_replicas_kernel stores for this q: C rotated by -q
+    const PfaRot rot = pfa_rotation<G>(-q);
+    std::vector<cf> crot((size_t)G::W);
+    for (int m = 0; m < G::W; m++) {
+        int a = m / G::NA; const int j = m - a * G::NA;
+        a += rot.da; if (a >= G::RA) a -= G::RA;
+        crot[(size_t)m] = cs_in[a * G::NA + pfa_rot_col<G>(j, rot)];
+    }
+    const cf *cs = crot.data();
     std::vector<cf> sm((size_t)G::SMEM_ELEMS);
     for (int j = 0; j < G::NA; j++) pfa_cell_passA<G>(j, xs, cs, sm.data());
     for (int j = 0; j < G::NB; j++) pfa_passB<G, +1>(j, sm.data());
@@ -202,14 +211,15 @@ int emu_pfa_order(int w, int *k_of_m)
     return -1;
 }
 
-// xs = conj(X), cs = C, both in (a,b,c)-linear order; y: W outputs in natural lag order
-int emu_pfa_cell(int w, const float *xs, const float *cs, float *y, float *best, int *besti, float *sum, int *n_slow)
+// xs = conj(X), cs = C, both in (a,b,c)-linear order; the replica operand is rotated by -q spectral bins first
+// (the cell of Doppler bin r + R*q, ga_pfa.h); y: W outputs in natural lag order
+int emu_pfa_cell(int w, const float *xs, const float *cs, int q, float *y, float *best, int *besti, float *sum, int *n_slow)
 {
     *n_slow = 0;
     switch (w) {
-    case 5456: emu_pfa_cell_t<P5456>((const cf *)xs, (const cf *)cs, (cf *)y, best, besti, sum, n_slow); return 0;
-    case 8184: emu_pfa_cell_t<P8184>((const cf *)xs, (const cf *)cs, (cf *)y, best, besti, sum, n_slow); return 0;
-    case 2800: emu_pfa_cell_t<P2800>((const cf *)xs, (const cf *)cs, (cf *)y, best, besti, sum, n_slow); return 0;
+    case 5456: emu_pfa_cell_t<P5456>((const cf *)xs, (const cf *)cs, q, (cf *)y, best, besti, sum, n_slow); return 0;
+    case 8184: emu_pfa_cell_t<P8184>((const cf *)xs, (const cf *)cs, q, (cf *)y, best, besti, sum, n_slow); return 0;
+    case 2800: emu_pfa_cell_t<P2800>((const cf *)xs, (const cf *)cs, q, (cf *)y, best, besti, sum, n_slow); return 0;
     }
     return -1;
 }

@@ -192,12 +192,21 @@ def test_pfa_kernel_math_replay_matches_numpy(W):
     y = np.fft.ifft(xs.astype(np.complex128)[inv] * cs.astype(np.complex128)[inv]) * W     # conj(X)*C, backward
     yy = np.zeros(W, np.complex64)
     best, bi, sm, slow = ctypes.c_float(), ctypes.c_int(), ctypes.c_float(), ctypes.c_int()
-    assert L.emu_pfa_cell(W, P(xs.view(np.float32)), P(cs.view(np.float32)), P(yy.view(np.float32)),
+    assert L.emu_pfa_cell(W, P(xs.view(np.float32)), P(cs.view(np.float32)), 0, P(yy.view(np.float32)),
                           ctypes.byref(best), ctypes.byref(bi), ctypes.byref(sm), ctypes.byref(slow)) == 0
     assert np.abs(yy - y).max() <= 3e-6 * np.abs(y).max()
     pw = np.abs(y) ** 2
     assert bi.value == int(pw.argmax()) and slow.value == 0
     assert abs(best.value / pw.max() - 1) < 1e-5 and abs(sm.value / pw.sum() - 1) < 1e-5
+    # Doppler bins a whole DFT bin apart share one forward transform: the cell of bin r + R*q multiplies X_r with the
+    # replica spectrum rotated by -q; its powers equal those of conj(X_r[k+q]) C[k] (the product is only shifted)
+    for q in (1, -1, 7, -100, 100):
+        pq = np.abs(np.fft.ifft(np.roll(xs.astype(np.complex128)[inv], -q) * cs.astype(np.complex128)[inv]) * W) ** 2
+        yr = np.zeros(W, np.complex64)
+        assert L.emu_pfa_cell(W, P(xs.view(np.float32)), P(cs.view(np.float32)), q, P(yr.view(np.float32)),
+                              ctypes.byref(best), ctypes.byref(bi), ctypes.byref(sm), ctypes.byref(slow)) == 0
+        assert np.abs(np.abs(yr.astype(np.complex128)) ** 2 - pq).max() <= 1e-5 * pq.max(), q
+        assert bi.value == int(pq.argmax())
     # exact ties: "first maximum wins" (c/search_offline.cpp:192) must not depend on the order the butterflies
     # produce their outputs in.  A flat product spectrum gives one peak at lag 0 and exact zeros elsewhere
     # is not guaranteed in floats, so use the two degenerate inputs whose powers are exactly equal:
@@ -207,7 +216,7 @@ def test_pfa_kernel_math_replay_matches_numpy(W):
         if fill == 1.0:
             cs[:] = 0.0
             cs[np.argsort(order)[0]] = 1.0            # only spectral bin k = 0 set: y[t] = 1 for every lag
-        L.emu_pfa_cell(W, P(xs.view(np.float32)), P(cs.view(np.float32)), P(yy.view(np.float32)),
+        L.emu_pfa_cell(W, P(xs.view(np.float32)), P(cs.view(np.float32)), 0, P(yy.view(np.float32)),
                        ctypes.byref(best), ctypes.byref(bi), ctypes.byref(sm), ctypes.byref(slow))
         assert bi.value == want and slow.value > 0
         assert best.value == fill and sm.value == fill * W
