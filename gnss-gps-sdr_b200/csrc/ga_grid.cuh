@@ -75,7 +75,7 @@ __global__ void grid_replica_extend_kernel(const float *__restrict__ code_w, int
 template <class G, int T, int NW, int GID>
 __global__ void __launch_bounds__(T, TM_MINB) grid_cell_kernel(const cf *__restrict__ xg, const cf *__restrict__ cext,
                                                                const cf *__restrict__ tw, int n_cells, int n_dop, int kblocks,
-                                                               int wlen, CellStat *__restrict__ cells)
+                                                               int wlen, int dmax, int n_base, CellStat *__restrict__ cells)
 {
     static_assert(T % 32 == 0, "tcgen05.ld/st are warp-collective: whole warps only");
     constexpr int NWARP = T / 32;
@@ -111,9 +111,22 @@ __global__ void __launch_bounds__(T, TM_MINB) grid_cell_kernel(const cf *__restr
         const cf *cb = cext + (size_t)prn * (2 * G::N);
         float best = 0.0f, sum = 0.0f;
         int besti = 0;
+        // exact-length transforms (N1 = 1, L = W) with n_base = R > 0: only the bins 0..R-1 of each block were
+        // transformed; bin d = r + R*q reads block spectrum r and the replica spectrum rotated by -q, which in the
+        // doubled natural-order layout is a pointer offset (see ga_pfa.h for why the powers are the same)
+        int xsel = di, xstride = n_dop;
+        if (G::N1 == 1 && n_base > 0) {
+            const int d = di - dmax;
+            int rr = d % n_base;
+            if (rr < 0) rr += n_base;
+            int off = -((d - rr) / n_base) % G::N2;
+            if (off < 0) off += G::N2;
+            xsel = rr; xstride = n_base;
+            cb += off;
+        }
 
         for (int k = 0; k < kblocks; k++) {
-            const cf *xb = xg + ((size_t)(acq * kblocks + k) * n_dop + di) * G::N;
+            const cf *xb = xg + ((size_t)(acq * kblocks + k) * xstride + xsel) * G::N;
             for (int s = 0; s < G::N1; s++) {
                 const cf *xs = xb + (size_t)s * G::N2;
                 const cf *cs = cb + (size_t)s * (2 * G::N2);

@@ -452,8 +452,9 @@ template <class H, int T, int NW, int HID> struct GridOps {
     }
     static int fwd_blocks(gpsacq *h, size_t n_blocks, const unsigned char *d_bits)
     {
-        fwd_grid_kernel<H, FWD_T, HID><<<(unsigned)(n_blocks * h->ndop * H::N1), FWD_T, h->cell_smem, h->stream>>>(
-            d_bits, h->block_bytes, h->d_lo, h->d_wipe, h->w, h->ndop, h->dmax, h->wipe_m, h->d_tw, h->d_xg);
+        const int items = h->n_base > 0 ? h->n_base : h->ndop, item_dmax = h->n_base > 0 ? 0 : h->dmax;     // see PfaOps::fwd_blocks
+        fwd_grid_kernel<H, FWD_T, HID><<<(unsigned)(n_blocks * items * H::N1), FWD_T, h->cell_smem, h->stream>>>(
+            d_bits, h->block_bytes, h->d_lo, h->d_wipe, h->w, items, item_dmax, h->wipe_m, h->d_tw, h->d_xg);
         CUDA_TRY(h, cudaGetLastError());
         return 0;
     }
@@ -462,7 +463,7 @@ template <class H, int T, int NW, int HID> struct GridOps {
         const int n_cells = (int)(n_acq * 32 * (size_t)h->ndop);
         const int grid = std::min(n_cells, h->cell_ctas);
         grid_cell_kernel<H, T, NW, HID><<<grid, T, h->cell_smem, h->stream>>>(h->d_xg, h->d_cext, h->d_tw, n_cells, h->ndop,
-                                                                            h->kblocks, h->w, h->d_cells);
+                                                                            h->kblocks, h->w, h->dmax, h->n_base, h->d_cells);
         CUDA_TRY(h, cudaGetLastError());
         return 0;
     }
@@ -508,7 +509,7 @@ template <class G, int T, int MINB, bool MULTI> struct PfaOps {
     {
         const int n_cells = (int)(n_acq * 32 * (size_t)h->ndop);
         const int grid = std::min(n_cells, h->cell_ctas);
-        pfa_cell_kernel<G, T, MINB, MULTI><<<grid, T, h->cell_smem, h->stream>>>(h->d_xg, h->n_base > 0 ? h->d_crot : h->d_cext, n_cells, h->ndop,
+        pfa_cell_kernel<G, T, MINB, MULTI><<<grid, T, h->cell_smem, h->stream>>>(h->d_xg, h->d_crot ? h->d_crot : h->d_cext, n_cells, h->ndop,
                                                                                  h->dmax, h->n_base, h->q_min, h->kblocks, h->d_cells);
         CUDA_TRY(h, cudaGetLastError());
         return 0;
@@ -604,7 +605,7 @@ static int create_grid(gpsacq *h)
     {
         const char *ns = getenv("GPSACQ_GRID_NOSHARE");
         const int r = h->w > 0 ? h->wipe_m / h->w : 0;
-        if (h->gid >= PID_5456 && !(ns && *ns && *ns != '0') && r >= 1 && (long long)r * h->w == h->wipe_m && r < h->ndop) h->n_base = r;
+        if ((h->gid >= PID_5456 || h->n1 == 1) && !(ns && *ns && *ns != '0') && r >= 1 && (long long)r * h->w == h->wipe_m && r < h->ndop) h->n_base = r;
     }
     // batch capacity: keep the block spectra of one batch under ~3 GB
     const size_t per_acq = (size_t)h->kblocks * (h->n_base > 0 ? h->n_base : h->ndop) * h->n * sizeof(cf);
@@ -661,7 +662,7 @@ static int create_grid(gpsacq *h)
     }
     rc = GRID_DISPATCH(h, replicas(h));
     if (rc) return rc;
-    if (h->n_base > 0) {
+    if (h->n_base > 0 && h->gid >= PID_5456) {
         // bins of this handle: d in [-dmax, -dmax + ndop); q = floor(d / R)
         const int d_lo = -h->dmax, d_hi = -h->dmax + h->ndop - 1;
         auto fdiv = [](int a, int b) { int q = a / b; return (a % b != 0 && (a < 0)) ? q - 1 : q; };

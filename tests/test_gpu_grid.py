@@ -130,6 +130,37 @@ def test_grid_doppler_shards_merge_to_the_full_grid(ga, siggen):
         ga.Acquisition(fc, fs, 10000.0, mode=1, doppler_step=250.0, dop_first=80, dop_count=5)
 
 
+@pytest.mark.parametrize("fs,fc,step,K", [(5.456e6, 4.092e6, 250.0, 2), (8.184e6, 2.046e6, 100.0, 1), (4.096e6, 1.0e6, 100.0, 2), (10e6, 2.6e6, 200.0, 1)])
+def test_grid_shared_forward_transforms_change_nothing(ga, siggen, monkeypatch, fs, fc, step, K):
+    """Doppler bins 1000/step apart share one forward transform and multiply with a rotated replica spectrum
+    (csrc/ga_pfa.h).  Against one transform per bin (GPSACQ_GRID_NOSHARE=1): same integers, powers within rounding."""
+    W = int(round(fs / 1000))
+    sats = siggen.default_constellation(fs, cn0_dbhz=50.0, seed=17, max_doppler=4500.0)
+    bits = siggen.synth_capture(W * K * 2, fs, fc, sats, seed=19)
+    res = {}
+    for name, env in (("shared", None), ("per_bin", "1")):
+        if env is None:
+            monkeypatch.delenv("GPSACQ_GRID_NOSHARE", raising=False)
+        else:
+            monkeypatch.setenv("GPSACQ_GRID_NOSHARE", env)
+        acq = ga.Acquisition(fc, fs, 5000.0, mode=1, doppler_step=step, noncoh_blocks=K)
+        try:
+            assert acq.info["fft_len"] == W
+            res[name] = (acq.acquire(bits).copy(), [acq.cell_stats(32 + p).copy() for p in (0, 12, 30)])
+        finally:
+            acq.close()
+    a, b = res["shared"], res["per_bin"]
+    det = b[0]["snr"] >= 25
+    assert det.sum() >= 3
+    assert np.array_equal(a[0]["lo_shift"][det], b[0]["lo_shift"][det])
+    assert np.array_equal(a[0]["ca_shift"][det], b[0]["ca_shift"][det])
+    assert np.abs(a[0]["snr"][det] / b[0]["snr"][det] - 1).max() <= 5e-5
+    for ca, cb in zip(a[1], b[1]):
+        assert np.abs(ca["max_pwr"] / cb["max_pwr"] - 1).max() <= 5e-5
+        assert np.abs(ca["tot_pwr"] / cb["tot_pwr"] - 1).max() <= 5e-5
+        assert (ca["max_idx"] != cb["max_idx"]).sum() <= 1
+
+
 # ---- BASELINE.json configs[3] / configs[4] at FULL size, through size-independent properties ------------------
 @pytest.mark.parametrize("fs,fc,step,nbins", [(2.8e6, 0.62e6, 250.0, 801), (8.184e6, 2.046e6, 100.0, 2001)])
 def test_grid_full_size_properties(ga, siggen, fs, fc, step, nbins):
