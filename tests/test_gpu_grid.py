@@ -130,6 +130,26 @@ def test_grid_doppler_shards_merge_to_the_full_grid(ga, siggen):
         ga.Acquisition(fc, fs, 10000.0, mode=1, doppler_step=250.0, dop_first=80, dop_count=5)
 
 
+@pytest.mark.parametrize("use_nccl", [True, False])
+def test_grid_group_api_matches_single_gpu(ga, siggen, use_nccl):
+    """gpsacq_group_acquire(): Doppler-bin ranges over the visible GPUs (2 when there are two, else one), one
+    ncclAllGather of the peak records per batch; records identical to a single-GPU handle's."""
+    import torch
+    n = min(torch.cuda.device_count(), 2)
+    fs, fc, K = 8.184e6, 2.046e6, 2
+    W = int(round(fs / 1000))
+    sats = siggen.default_constellation(fs, cn0_dbhz=50.0, seed=23, max_doppler=9000.0)
+    bits = siggen.synth_capture(W * K * 3, fs, fc, sats, seed=29)
+    with ga.Acquisition(fc, fs, 10000.0, mode=1, doppler_step=100.0, noncoh_blocks=K) as one:
+        want = one.acquire(bits).copy()
+    grp = ga.AcquisitionGroup(fc, fs, 10000.0, n_gpus=n, use_nccl=use_nccl, mode=1, doppler_step=100.0, noncoh_blocks=K)
+    try:
+        assert grp.gather_kind == ("nccl" if (use_nccl and n > 1) else "host")
+        assert grp.acquire(bits).tobytes() == want.tobytes()
+    finally:
+        grp.close()
+
+
 @pytest.mark.parametrize("fs,fc,step,K", [(5.456e6, 4.092e6, 250.0, 2), (8.184e6, 2.046e6, 100.0, 1), (4.096e6, 1.0e6, 100.0, 2), (10e6, 2.6e6, 200.0, 1)])
 def test_grid_shared_forward_transforms_change_nothing(ga, siggen, monkeypatch, fs, fc, step, K):
     """Doppler bins 1000/step apart share one forward transform and multiply with a rotated replica spectrum
