@@ -81,8 +81,16 @@ struct RealSrc {      // SearchInit(): real replica, imaginary part 0 (:101-102)
 };
 
 // MODE 0: blocks -> conj(X) into xd[item][s][q].   MODE 1: replicas -> cext[item][s][q] and [q+N2].
+// MODE 0 stores through shared memory: a pass-C thread holds outputs q = tau0 + RA*RB*w, 160 bytes apart from its
+// neighbour's -- written straight to HBM every 8-byte store would touch its own 32-byte sector.  Each thread puts
+// its RC outputs back into the row it has just read (nobody else touches that row), and after a barrier the CTA
+// streams the N2 values out in natural order with coalesced float2 stores (the read side walks shared memory with
+// the odd stride Q: conflict-free).
+#ifndef FWD_MINB
+#define FWD_MINB 2     // measured: 2 CTAs/SM at 126 registers beat 3 at 80 (spills)
+#endif
 template <class G, int T, int MODE, int GID>
-__global__ void __launch_bounds__(T) fwd_kernel(const unsigned char *__restrict__ bits, int chunk_bytes,
+__global__ void __launch_bounds__(T, MODE == 0 ? FWD_MINB : 1) fwd_kernel(const unsigned char *__restrict__ bits, int chunk_bytes,
                                                 const unsigned char *__restrict__ lo,
                                                 const float *__restrict__ repl_time,
                                                 const cf *__restrict__ tw, cf *__restrict__ out)
@@ -102,14 +110,26 @@ __global__ void __launch_bounds__(T) fwd_kernel(const unsigned char *__restrict_
     __syncthreads();
     for (int j = threadIdx.x; j < G::NB; j += T) passB<G, -1>(j, 0, tw, sm);
     __syncthreads();
-    for (int j = threadIdx.x; j < G::NC; j += T) {
-        cf p[G::RC];
-        const int tau0 = passC<G, -1>(j, sm, p);
-        if (MODE == 0) {
-            cf *dst = out + ((size_t)item * G::N1 + s) * G::N2 + tau0;
+    if (MODE == 0) {
+        for (int j = threadIdx.x; j < G::NC; j += T) {
+            cf p[G::RC];
+            passC<G, -1>(j, sm, p);
+            const int u = j / G::RB, v = j - u * G::RB;
+            cf *row = sm + G::template sa<0>() * u + G::template sb<0>() * v;
 #pragma unroll
-            for (int w = 0; w < G::RC; w++) dst[G::OUT_STRIDE * w] = cconj(p[w]);
-        } else {
+            for (int w = 0; w < G::RC; w++) row[w] = cconj(p[w]);
+        }
+        __syncthreads();
+        cf *dst = out + ((size_t)item * G::N1 + s) * G::N2;
+        for (int q = threadIdx.x; q < G::N2; q += T) {           // q = u + RA*v + RA*RB*w
+            const int w = q / G::OUT_STRIDE, r = q - w * G::OUT_STRIDE;
+            const int v = r / G::RA, u = r - v * G::RA;
+            dst[q] = sm[G::template sa<0>() * u + G::template sb<0>() * v + w];
+        }
+    } else {
+        for (int j = threadIdx.x; j < G::NC; j += T) {
+            cf p[G::RC];
+            const int tau0 = passC<G, -1>(j, sm, p);
             cf *dst = out + ((size_t)item * G::N1 + s) * (2 * G::N2) + tau0;
 #pragma unroll
             for (int w = 0; w < G::RC; w++) { dst[G::OUT_STRIDE * w] = p[w]; dst[G::N2 + G::OUT_STRIDE * w] = p[w]; }

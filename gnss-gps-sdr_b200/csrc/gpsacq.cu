@@ -103,7 +103,9 @@ enum { XID_10000 = 7, XID_8000 = 8, XID_4000 = 9, XID_4096 = 10, XID_2048 = 11 }
 #define CELL_T_8000 448     // 14 whole warps, one 32-butterfly task each (13 tasks per pass), 72 registers, 2 CTAs/SM
 #endif
 #define CELL_T_10000 256
+#ifndef FWD_T
 #define FWD_T 256
+#endif
 
 static const double kCPS = 1.023e6;    // chip rate, c/gps_offline.h:30
 
