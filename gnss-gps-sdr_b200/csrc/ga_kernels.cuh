@@ -225,6 +225,7 @@ __global__ void __launch_bounds__(T, TM_MINB) cell_kernel_tm(const cf *__restric
     // four sub-partitions was measured: no gain, and it made the summation order depend on the CTA.)
     constexpr int NTA = cdiv(G::NA, 32), NTB = cdiv(G::NB, 32), NTC = cdiv(G::NC, 32);
     constexpr int ITA = cdiv(NTA, NWARP), ITB = cdiv(NTB, NWARP), ITC = cdiv(NTC, NWARP);
+    constexpr bool SPLIT_C = T <= 256;                             // see pass C: only where 128 registers are available (2 x 256 threads)
     constexpr uint32_t COLS_THREAD = ITC * 2 * NW;                 // accumulator floats per thread
     constexpr uint32_t COL_SLOT = (COLS_THREAD + 7u) & ~7u;        // column range of one warp "row" (4 warps share the lanes)
     constexpr uint32_t TM_COLS = pow2_at_least(COL_SLOT * cdiv(NWARP, 4));
@@ -288,25 +289,25 @@ GA_IT_PRAGMA
                     const int jc = act ? j : G::NC - 1;
                     cf p[G::RC];
                     const int tau0 = passC<G, +1>(jc, sm, p);
-                    float a[2 * NW];
                     const uint32_t col = tm_mine + (uint32_t)(it * 2 * NW);
-                    if (s == 0) {
+                    // acc = TMEM accumulators + p * ktab[s]
+                    auto accumulate = [&](float (&a)[2 * NW]) {
+                        if (s == 0) {
 #pragma unroll
-                        for (int w = 0; w < NW; w++) { a[2 * w] = p[w].x; a[2 * w + 1] = p[w].y; }   // ktab[0][w] = 1
-                    } else {
-                        tm_move<2 * NW, true>(col, a);
-                        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                            for (int w = 0; w < NW; w++) { a[2 * w] = p[w].x; a[2 * w + 1] = p[w].y; }   // ktab[0][w] = 1
+                        } else {
+                            tm_move<2 * NW, true>(col, a);
+                            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
-                        for (int w = 0; w < NW; w++) {
-                            cf t = mk(a[2 * w], a[2 * w + 1]);
-                            cfma(t, p[w], ks[w]);
-                            a[2 * w] = t.x; a[2 * w + 1] = t.y;
+                            for (int w = 0; w < NW; w++) {
+                                cf t = mk(a[2 * w], a[2 * w + 1]);
+                                cfma(t, p[w], ks[w]);
+                                a[2 * w] = t.x; a[2 * w + 1] = t.y;
+                            }
                         }
-                    }
-                    if (s < G::N1 - 1) {
-                        tm_move<2 * NW, false>(col, a);
-                    } else if (act) {
-                        // last sub-sequence: the outputs are complete -> power, first max, sum (:190-194)
+                    };
+                    // last sub-sequence: the outputs are complete -> power, first max, sum (:190-194)
+                    auto peak = [&](const float (&a)[2 * NW]) {
 #pragma unroll
                         for (int w = 0; w < NW; w++) {
                             const int tau = tau0 + G::OUT_STRIDE * w;
@@ -316,6 +317,24 @@ GA_IT_PRAGMA
                                 sum += pwr;
                             }
                         }
+                    };
+                    if constexpr (SPLIT_C) {
+                        // store path and power path as separate code: their registers are allocated independently and
+                        // the compiler needs no copies between them (-5 % instructions; needs register headroom)
+                        if (s < G::N1 - 1) {
+                            float a[2 * NW];
+                            accumulate(a);
+                            tm_move<2 * NW, false>(col, a);
+                        } else {
+                            float a[2 * NW];
+                            accumulate(a);
+                            if (act) peak(a);
+                        }
+                    } else {
+                        float a[2 * NW];
+                        accumulate(a);
+                        if (s < G::N1 - 1) tm_move<2 * NW, false>(col, a);
+                        else if (act) peak(a);
                     }
                 }
             }
