@@ -29,9 +29,22 @@ def test_c_abi_exports_every_declared_symbol(ga):
     ga.load_library()
 
 
-def test_struct_layouts_match_header(ga):
+def test_struct_layouts_match_header(ga, tmp_path):
     assert ga.PEAK_DTYPE.itemsize == 32 and ga.CELL_DTYPE.itemsize == 16
     assert ga.PEAK_DTYPE.fields["ca_shift"][1] == 16 and ga.PEAK_DTYPE.fields["flags"][1] == 24
+    # the ctypes / numpy mirrors against what a C compiler makes of include/gpsacq.h
+    from gnss_gps_sdr_b200 import acq
+    src = tmp_path / "sizes.c"
+    src.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "gpsacq.h"\nint main(void){printf("%zu %zu %zu %zu %zu %zu %zu %zu %d\\n",'
+                   'sizeof(gpsacq_cfg), sizeof(gpsacq_info), sizeof(gpsacq_peak), sizeof(gpsacq_cell), sizeof(gpsacq_handoff),'
+                   'sizeof(gpsacq_event), offsetof(gpsacq_event, start), sizeof(gpsacq_sat), GPSACQ_ABI_VERSION);return 0;}\n')
+    exe = tmp_path / "sizes"
+    subprocess.run(["gcc", f"-I{ROOT / 'include'}", str(src), "-o", str(exe)], check=True)
+    got = [int(v) for v in subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.split()]
+    want = [ctypes.sizeof(acq._Cfg), ctypes.sizeof(acq._Info), ga.PEAK_DTYPE.itemsize, ga.CELL_DTYPE.itemsize,
+            ga.HANDOFF_DTYPE.itemsize, ga.EVENT_DTYPE.itemsize, ga.EVENT_DTYPE.fields["start"][1], ctypes.sizeof(acq._Sat), 3]
+    assert got == want, (got, want)
+    assert ctypes.sizeof(acq._Handoff) == ga.HANDOFF_DTYPE.itemsize
 
 
 def test_no_cpu_fallback(ga, gpu_available):
