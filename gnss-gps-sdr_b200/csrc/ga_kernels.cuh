@@ -206,15 +206,24 @@ constexpr uint32_t pow2_at_least(uint32_t x, uint32_t p = 32) { return p >= x ? 
 #define TM_MINB 2     // CTAs per SM the TMEM kernel is sized for
 #endif
 
-// task loops of cell_kernel_tm: fully unrolled (one task per warp in the default 448-thread shape); CTA shapes with
-// several tasks per warp (experiments) must not unroll, or the compiler hoists every task's loads and spills
-#ifdef GA_IT_UNROLL1
-#define GA_IT_PRAGMA _Pragma("unroll 1")
-#else
-#define GA_IT_PRAGMA _Pragma("unroll")
-#endif
+// Task loop of a warp (task = 32 butterflies): unrolled when a warp has at most two tasks per pass; with more (the
+// 128-thread shape) NOT unrolled, or the compiler hoists every task's operand loads and spills.
+template <int IT, class F> __device__ __forceinline__ void for_tasks(F &&f)
+{
+    if constexpr (IT <= 2) {
+#pragma unroll
+        for (int it = 0; it < IT; it++) f(it);
+    } else {
+#pragma unroll 1
+        for (int it = 0; it < IT; it++) f(it);
+    }
+}
+// CTAs per SM a cell-kernel shape is sized for: 128-thread CTAs run three per SM (201 KB of shared memory, 136
+// registers), the 256/448-thread shapes two
+constexpr int cell_minb(int threads) { return threads <= 128 ? 3 : 2; }
+
 template <class G, int T, int NW, int GID>
-__global__ void __launch_bounds__(T, TM_MINB) cell_kernel_tm(const cf *__restrict__ xd, const cf *__restrict__ cext,
+__global__ void __launch_bounds__(T, cell_minb(T)) cell_kernel_tm(const cf *__restrict__ xd, const cf *__restrict__ cext,
                                                        const int *__restrict__ sv_of_block, const cf *__restrict__ tw,
                                                        int n_cells, int n_dop, int dmax, int wlen, CellStat *__restrict__ cells)
 {
@@ -230,8 +239,8 @@ __global__ void __launch_bounds__(T, TM_MINB) cell_kernel_tm(const cf *__restric
     constexpr uint32_t COL_SLOT = (COLS_THREAD + 7u) & ~7u;        // column range of one warp "row" (4 warps share the lanes)
     constexpr uint32_t TM_COLS = pow2_at_least(COL_SLOT * cdiv(NWARP, 4));
 #ifndef GA_NO_TM_ASSERT
-    static_assert(TM_COLS * TM_MINB <= 512 || G::SMEM_ELEMS * sizeof(cf) * TM_MINB > 227 * 1024,
-                  "TM_MINB CTAs per SM must fit in the 512 TMEM columns");
+    static_assert(TM_COLS * cell_minb(T) <= 512 || G::SMEM_ELEMS * sizeof(cf) * cell_minb(T) > 227 * 1024,
+                  "cell_minb(T) CTAs per SM must fit in the 512 TMEM columns");
 #endif
     extern __shared__ __align__(16) unsigned char smem_raw[];
     cf *sm = reinterpret_cast<cf *>(smem_raw);
@@ -265,21 +274,18 @@ __global__ void __launch_bounds__(T, TM_MINB) cell_kernel_tm(const cf *__restric
             cell_sub_offsets<G>(s, dop, sp, eoff);
             const cf *xs = xb + (size_t)s * G::N2;
             const cf *cs = cb + (size_t)sp * (2 * G::N2) + eoff;
-GA_IT_PRAGMA
-            for (int it = 0; it < ITA; it++) {
+            for_tasks<ITA>([&](int it) {
                 const int j = (vw + it * NWARP) * 32 + lane;
                 if (j < G::NA) cell_passA<G>(j, s, xs, cs, tw, sm);
-            }
+            });
             __syncthreads();
-GA_IT_PRAGMA
-            for (int it = 0; it < ITB; it++) {
+            for_tasks<ITB>([&](int it) {
                 const int j = (vw + it * NWARP) * 32 + lane;
                 if (j < G::NB) passB<G, +1>(j, s, tw, sm);
-            }
+            });
             __syncthreads();
             const cf *ks = c_ktab[GID] + s * G::RC;
-GA_IT_PRAGMA
-            for (int it = 0; it < ITC; it++) {
+            for_tasks<ITC>([&](int it) {
                 const int task = vw + it * NWARP;
                 if (task < NTC) {          // warp-uniform
                     // every lane runs the butterfly (lanes past the end redo the last one) so that the
@@ -337,7 +343,7 @@ GA_IT_PRAGMA
                         else if (act) peak(a);
                     }
                 }
-            }
+            });
             asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
             __syncthreads();      // smem is rewritten by the next sub-sequence's pass A
         }

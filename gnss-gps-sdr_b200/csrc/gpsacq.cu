@@ -100,8 +100,10 @@ enum { XID_10000 = 7, XID_8000 = 8, XID_4000 = 9, XID_4096 = 10, XID_2048 = 11 }
 
 #define CELL_T_4000 256
 #ifndef CELL_T_8000
-#define CELL_T_8000 448     // 14 whole warps, one 32-butterfly task each (13 tasks per pass), 72 registers, 2 CTAs/SM
+#define CELL_T_8000 128     // 4 warps (one per SM sub-partition) x 3 CTAs/SM, 13 tasks per pass dealt over the warps, 136 registers;
+                            // 448 threads x 2 CTAs (one task per warp, 72 registers) measures 1.7 % slower
 #endif
+#define CELL_T_8000_WIDE 448  // search windows above 5600 samples (20 accumulators per butterfly): too many TMEM columns for 3 CTAs/SM
 #define CELL_T_10000 256
 #ifndef FWD_T
 #define FWD_T 256
@@ -208,18 +210,19 @@ static int setup_cells_t(gpsacq *h)
     h->cell_nw = NW;
     CUDA_TRY(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, h->cell_smem));
     // ask for a shared-memory carveout that fits two CTAs (the rest stays L1 for the operand loads)
-    const int want = CELL_MINB * (h->cell_smem + 2048);
+    constexpr int MINB = cell_minb(T);
+    const int want = MINB * (h->cell_smem + 2048);
     int pct = (int)((want * 100LL + 228 * 1024 - 1) / (228 * 1024));
-    if (pct > 100) pct = 100;
+    if (pct > 88) pct = 100;
     CUDA_TRY(h, cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, pct));
     int per_sm = 0;
     CUDA_TRY(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, T, h->cell_smem));
     if (per_sm < 1) { h->err = "cell kernel does not fit on an SM"; return GPSACQ_ECUDA; }
     // The occupancy query is conservative for kernels that allocate tensor memory (it cannot see the
     // column count, a run-time operand of tcgen05.alloc, and reports one CTA per SM).  Registers and
-    // shared memory are sized for CELL_MINB CTAs (__launch_bounds__, carveout above) and each CTA
-    // allocates at most 256 of the 512 TMEM columns, so CELL_MINB CTAs are resident.
-    if (GA_CELL_TMEM != 0 && !G::ROT && T % 32 == 0 && per_sm < CELL_MINB) per_sm = CELL_MINB;
+    // shared memory are sized for cell_minb(T) CTAs (__launch_bounds__, carveout above) and each CTA
+    // allocates at most 512 / cell_minb(T) TMEM columns, so that many CTAs are resident.
+    if (GA_CELL_TMEM != 0 && !G::ROT && T % 32 == 0 && per_sm < MINB) per_sm = MINB;
     h->cell_ctas = per_sm * h->sm_count;
     return 0;
 }
@@ -244,7 +247,7 @@ static int setup_cells(gpsacq *h)
                                              : setup_cells_t<G4000, CELL_T_4000, 10, GID_4000>(h);
     case GID_8000:
         return h->w <= 14 * G8000::OUT_STRIDE ? setup_cells_t<G8000, CELL_T_8000, 14, GID_8000>(h)
-                                              : setup_cells_t<G8000, CELL_T_8000, 20, GID_8000>(h);
+                                              : setup_cells_t<G8000, CELL_T_8000_WIDE, 20, GID_8000>(h);
     default:
         return h->w <= 17 * G10000::OUT_STRIDE ? setup_cells_t<G10000, CELL_T_10000, 17, GID_10000>(h)
                                                : setup_cells_t<G10000, CELL_T_10000, 20, GID_10000>(h);
@@ -259,7 +262,7 @@ static int launch_cells(gpsacq *h, size_t n_blocks, const int *d_sv, size_t off 
                                : launch_cells_t<G4000, CELL_T_4000, 10, GID_4000>(h, n_blocks, d_sv, off);
     case GID_8000:
         return h->cell_nw == 14 ? launch_cells_t<G8000, CELL_T_8000, 14, GID_8000>(h, n_blocks, d_sv, off)
-                                : launch_cells_t<G8000, CELL_T_8000, 20, GID_8000>(h, n_blocks, d_sv, off);
+                                : launch_cells_t<G8000, CELL_T_8000_WIDE, 20, GID_8000>(h, n_blocks, d_sv, off);
     default:
         return h->cell_nw == 17 ? launch_cells_t<G10000, CELL_T_10000, 17, GID_10000>(h, n_blocks, d_sv, off)
                                 : launch_cells_t<G10000, CELL_T_10000, 20, GID_10000>(h, n_blocks, d_sv, off);
