@@ -98,13 +98,17 @@ enum { XID_10000 = 7, XID_8000 = 8, XID_4000 = 9, XID_4096 = 10, XID_2048 = 11 }
 #define PFA_B_2800 5
 #endif
 
-#define CELL_T_4000 256
+#ifndef CELL_T_4000
+#define CELL_T_4000 128     // 3 CTAs/SM like the benchmark geometry (+3 % over 256 x 2)
+#endif
 #ifndef CELL_T_8000
 #define CELL_T_8000 128     // 4 warps (one per SM sub-partition) x 3 CTAs/SM, 13 tasks per pass dealt over the warps, 136 registers;
                             // 448 threads x 2 CTAs (one task per warp, 72 registers) measures 1.7 % slower
 #endif
 #define CELL_T_8000_WIDE 448  // search windows above 5600 samples (20 accumulators per butterfly): too many TMEM columns for 3 CTAs/SM
+#ifndef CELL_T_10000
 #define CELL_T_10000 256
+#endif
 #ifndef FWD_T
 #define FWD_T 256
 #endif
