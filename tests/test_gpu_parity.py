@@ -177,7 +177,10 @@ def test_rejects_unsupported_configs(ga):
 
 
 # ---- other sampling rates, synthetic captures (no reference fixture exists) --------------------------------
-@pytest.mark.parametrize("fs,fc,seed", [(2.8e6, 0.62e6, 1575420001), (10e6, 2.6e6, 3), (5.456e6, 4.092e6, 1575420000)])
+# (8 MHz and 4 MHz exercise the wide-window variants of the 8000- and 4000-point geometries: 20 / 10 accumulators per
+# butterfly, 448-thread and 128-thread CTA shapes)
+@pytest.mark.parametrize("fs,fc,seed", [(2.8e6, 0.62e6, 1575420001), (10e6, 2.6e6, 3), (5.456e6, 4.092e6, 1575420000),
+                                        (8.0e6, 2.0e6, 11), (4.0e6, 1.0e6, 12)])
 def test_synthetic_vs_oracle(engines, oracle_mod, siggen, fs, fc, seed):
     sats = siggen.default_constellation(fs, seed=seed)
     bits = siggen.synth_capture(40960 * 32, fs, fc, sats, seed=seed)
