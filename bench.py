@@ -217,6 +217,9 @@ def run_engine(args, rank, world, local_rank):
     ga = gpsacq_loader.load()
     dist = None
     if world > 1:
+        # NCCL prints its version banner (and any NCCL_DEBUG output) to stdout by default: keep stdout for the one
+        # JSON line of the contract
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         import torch.distributed as dist
         torch.cuda.set_device(local_rank)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
