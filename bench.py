@@ -216,10 +216,13 @@ def run_engine(args, rank, world, local_rank):
     import gpsacq_loader
     ga = gpsacq_loader.load()
     dist = None
+    json_fd = None
     if world > 1:
-        # NCCL prints its version banner (and any NCCL_DEBUG output) to stdout by default: keep stdout for the one
-        # JSON line of the contract
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+        # NCCL writes its version banner (NCCL_DEBUG=VERSION/WARN) to file descriptor 1.  The contract wants ONE JSON
+        # line on stdout: send everything else that lands on fd 1 to stderr and keep a private handle for the line.
+        sys.stdout.flush()
+        json_fd = os.dup(1)
+        os.dup2(2, 1)
         import torch.distributed as dist
         torch.cuda.set_device(local_rank)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
@@ -344,7 +347,11 @@ def run_engine(args, rank, world, local_rank):
             cb, _, _ = cpu_baseline(runs_per_core=4)
             os.unlink(cpu_sample_file())
             line["cpu_baseline"] = cb
-        print(json.dumps(line))
+        if json_fd is None:
+            print(json.dumps(line))
+        else:
+            sys.stdout.flush()
+            os.write(json_fd, (json.dumps(line) + "\n").encode())
     acq.close()
     if world > 1:
         dist.destroy_process_group()
