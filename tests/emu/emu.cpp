@@ -158,6 +158,8 @@ typedef PGeom<16, 25, 7> P2800;
 typedef Geom<5, 20, 20, 20, true> G8000;
 typedef Geom<4, 25, 20, 20> G10000;
 typedef Geom<10, 20, 20, 10> G4000;
+typedef Geom<2, 20, 20, 16> H6400;      // GRID: zero-padded embedding, L = 12800
+typedef Geom<1, 16, 16, 16> X4096;      // GRID: exact-length twiddled transform, L = W = 4096
 
 extern "C" {
 
@@ -167,6 +169,8 @@ int emu_geom(int id, int *n1, int *n2)
     case 0: *n1 = G8000::N1; *n2 = G8000::N2; return 0;
     case 1: *n1 = G10000::N1; *n2 = G10000::N2; return 0;
     case 2: *n1 = G4000::N1; *n2 = G4000::N2; return 0;
+    case 3: *n1 = H6400::N1; *n2 = H6400::N2; return 0;
+    case 4: *n1 = X4096::N1; *n2 = X4096::N2; return 0;
     }
     return -1;
 }
@@ -178,6 +182,8 @@ int emu_cell(int id, const float *xd_blk, const float *cext_sv, int dop, int wle
     case 0: emu_cell_t<G8000>((const cf *)xd_blk, (const cf *)cext_sv, dop, wlen, (cf *)y, best, besti, sum); return 0;
     case 1: emu_cell_t<G10000>((const cf *)xd_blk, (const cf *)cext_sv, dop, wlen, (cf *)y, best, besti, sum); return 0;
     case 2: emu_cell_t<G4000>((const cf *)xd_blk, (const cf *)cext_sv, dop, wlen, (cf *)y, best, besti, sum); return 0;
+    case 3: emu_cell_t<H6400>((const cf *)xd_blk, (const cf *)cext_sv, dop, wlen, (cf *)y, best, besti, sum); return 0;
+    case 4: emu_cell_t<X4096>((const cf *)xd_blk, (const cf *)cext_sv, dop, wlen, (cf *)y, best, besti, sum); return 0;
     }
     return -1;
 }
@@ -231,6 +237,8 @@ int emu_fwd(int id, const float *x, int s, float *out)
     case 0: emu_fwd_t<G8000>((const cf *)x, s, (cf *)out); return 0;
     case 1: emu_fwd_t<G10000>((const cf *)x, s, (cf *)out); return 0;
     case 2: emu_fwd_t<G4000>((const cf *)x, s, (cf *)out); return 0;
+    case 3: emu_fwd_t<H6400>((const cf *)x, s, (cf *)out); return 0;
+    case 4: emu_fwd_t<X4096>((const cf *)x, s, (cf *)out); return 0;
     }
     return -1;
 }

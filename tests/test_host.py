@@ -145,7 +145,9 @@ def _emu():
     return L
 
 
-@pytest.mark.parametrize("gid,W", [(0, 5456), (1, 8184), (2, 2800)])
+# gid 0-2: the three REF geometries (N = 40000); 3: a GRID embedding geometry (N1 = 2, L = 12800); 4: a GRID exact-length
+# geometry (N1 = 1, L = W = 4096)
+@pytest.mark.parametrize("gid,W", [(0, 5456), (1, 8184), (2, 2800), (3, 5456), (4, 4096)])
 def test_kernel_math_replay_matches_numpy(gid, W):
     L = _emu()
     fp = ctypes.POINTER(ctypes.c_float)
@@ -154,7 +156,7 @@ def test_kernel_math_replay_matches_numpy(gid, W):
     assert L.emu_geom(gid, ctypes.byref(n1), ctypes.byref(n2)) == 0
     N1, N2 = n1.value, n2.value
     N = N1 * N2
-    assert N == 40000 and W <= N2
+    assert N == (40000 if gid < 3 else 12800 if gid == 3 else 4096) and W <= N2
     rng = np.random.default_rng(gid)
     x = (rng.standard_normal(N) + 1j * rng.standard_normal(N)).astype(np.complex64)
     X = np.fft.fft(x.astype(np.complex128))
@@ -167,7 +169,7 @@ def test_kernel_math_replay_matches_numpy(gid, W):
     xd = np.conj(Xs).reshape(N2, N1).T.copy()
     cd = Cc.reshape(N2, N1).T
     cext = np.concatenate([cd, cd], axis=1).copy()
-    for dop in (-36, -1, 0, 5, 36):
+    for dop in ((-36, -1, 0, 5, 36) if gid < 3 else (0, -3, 7)):
         # prod[k] = conj(X[k]) * C[(k - dop) mod N]  (c/search_offline.cpp:181-185), backward FFT (:187)
         y = np.fft.ifft(np.conj(Xs.astype(np.complex128)) * np.roll(Cc.astype(np.complex128), dop)) * N
         yy = np.zeros(N2, np.complex64)
