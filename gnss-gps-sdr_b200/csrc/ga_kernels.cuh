@@ -222,6 +222,12 @@ template <int IT, class F> __device__ __forceinline__ void for_tasks(F &&f)
 // registers), the 256/448-thread shapes two
 constexpr int cell_minb(int threads) { return threads <= 128 ? 3 : 2; }
 
+// (400 butterflies per pass are 13 warp-tasks, so one of a CTA's four warps runs 4 tasks per pass and the others 3.
+// Warps sit on sub-partition (hardware warp slot mod 4); the hardware hands co-resident CTAs staggered warp slots
+// (0-3 / 5,6,7,4 / 10,11,8,9 -- tools/ubench/warpmap.cu), so the three heavy warps of an SM already land on three
+// different sub-partitions: 10/10/10/9 tasks per pass round.  Rotating the warp -> task map per CTA on top of that
+// was measured at -10 %: it re-aligns the heavy warps onto one sub-partition.)
+
 template <class G, int T, int NW, int GID>
 __global__ void __launch_bounds__(T, cell_minb(T)) cell_kernel_tm(const cf *__restrict__ xd, const cf *__restrict__ cext,
                                                        const int *__restrict__ sv_of_block, const cf *__restrict__ tw,

@@ -62,6 +62,8 @@ def _lib() -> C.CDLL:
     lib.oracle_grid_window.argtypes = [vp]
     lib.oracle_grid_acquire.restype = C.c_int
     lib.oracle_grid_acquire.argtypes = [vp, vp, vp, vp, vp, vp]
+    lib.oracle_grid_acquire_svs.restype = C.c_int
+    lib.oracle_grid_acquire_svs.argtypes = [vp, vp, vp, C.c_int, vp, vp, vp, vp]
     return lib
 
 
@@ -176,19 +178,25 @@ class GridOracle:
         except Exception:
             pass
 
-    def acquire(self, bits, want_cells: bool = False):
+    def acquire(self, bits, want_cells: bool = False, svs=None):
+        """svs: optional list of 0-based PRN indices (default all 32); records / cell rows come in that order."""
         buf = np.ascontiguousarray(np.frombuffer(bits, np.uint8) if not isinstance(bits, np.ndarray) else bits)
         n_acq = buf.size // self.acq_bytes
-        out = np.zeros(n_acq * 32, PEAK_DTYPE)
+        sv = np.arange(32, dtype=np.int32) if svs is None else np.ascontiguousarray(svs, np.int32)
+        ns = len(sv)
+        out = np.zeros(n_acq * ns, PEAK_DTYPE)
         cells = []
         for a in range(n_acq):
-            cm = np.zeros((32, self.n_doppler), np.float32)
-            ci = np.zeros((32, self.n_doppler), np.int32)
-            ct = np.zeros((32, self.n_doppler), np.float32)
+            cm = np.zeros((ns, self.n_doppler), np.float32)
+            ci = np.zeros((ns, self.n_doppler), np.int32)
+            ct = np.zeros((ns, self.n_doppler), np.float32)
             sub = np.ascontiguousarray(buf[a * self.acq_bytes:(a + 1) * self.acq_bytes])
-            one = np.zeros(32, PEAK_DTYPE)
-            self._l.oracle_grid_acquire(self._h, sub.ctypes.data, one.ctypes.data, cm.ctypes.data, ci.ctypes.data, ct.ctypes.data)
-            out[a * 32:(a + 1) * 32] = one
+            one = np.zeros(ns, PEAK_DTYPE)
+            rc = self._l.oracle_grid_acquire_svs(self._h, sub.ctypes.data, sv.ctypes.data, ns, one.ctypes.data,
+                                                 cm.ctypes.data, ci.ctypes.data, ct.ctypes.data)
+            if rc:
+                raise MemoryError("oracle_grid_acquire_svs failed")
+            out[a * ns:(a + 1) * ns] = one
             cells.append((cm, ci, ct))
         return (out, cells) if want_cells else out
 

@@ -1,12 +1,13 @@
 """GPU parity tests (run with `-m gpu` on a B200): the CUDA engine, called through the C ABI,
 against (a) golden vectors produced by the unmodified reference and (b) the CPU oracle."""
 import importlib
+import json
 import subprocess
 
 import numpy as np
 import pytest
 
-from conftest import CAPTURES, ROOT, SNR_RTOL, compare_peaks, compare_runs, parse_stdout, strip_banner
+from conftest import CAPTURES, GOLD, ROOT, SNR_RTOL, compare_peaks, compare_runs, parse_stdout, strip_banner
 
 pytestmark = pytest.mark.gpu
 PKG = ROOT / "gnss-gps-sdr_b200"
@@ -133,18 +134,87 @@ def test_gps_test_binary_vs_golden_stdout(name):
     compare_runs(got_runs, ref_runs[: c["runs"]])
 
 
-def test_full_capture_if_present(ga, engines):
-    """All 340 runs of the Nottingham capture when the 55 MB file travelled with the repo
-    (oracle/_ref/data/, git-ignored)."""
-    f = ROOT / "oracle" / "_ref" / "data" / "gps.samples.1bit.I.fs5456.if4092.bin"
-    if not f.exists():
-        pytest.skip("full capture not staged")
+# ---- the whole bundled capture (north_star acceptance; README.md:61, c/search_offline.cpp:219-292) ----------
+FULL_CAPTURE = ROOT / "oracle" / "_ref" / "data" / "gps.samples.1bit.I.fs5456.if4092.bin"      # staged by `make -C oracle`
+FULL_PEAKS = GOLD / "ref_peaks_nottingham_full.npy"          # the reference's Sample()+Correlate() on all 10,880 chunks
+STRIDED = GOLD / "nottingham_strided_runs.bin"               # whole runs 100-103, 200-203, 336-339 (always in the repo)
+RUN_BYTES = 32 * 5120
+
+
+def _capture_slices():
+    """(label, bytes, run numbers): the whole 340-run capture when it travelled with the repository (it is
+    git-ignored but NOT gpurun-ignored), and in any case the committed strided runs -- never a skip."""
+    runs = json.loads((GOLD / "nottingham_strided_runs.json").read_text())["runs"]
+    out = [("strided", STRIDED.read_bytes(), runs)]
+    if FULL_CAPTURE.exists():
+        out.append(("full", FULL_CAPTURE.read_bytes()[: 340 * RUN_BYTES], list(range(340))))   # + a partial 341st run ("run out of file!")
+    return out
+
+
+def _renumber(runs, numbers):
+    return [dict(r, run=numbers[i]) for i, r in enumerate(runs)]
+
+
+def test_whole_capture_peaks_vs_reference(engines):
+    """Every chunk's (snr, lo_shift, ca_shift) against what the UNMODIFIED reference returned for it
+    (tests/golden/ref_peaks_nottingham_full.npy): all 10,880 chunks when the capture is staged."""
     c = CAPTURES["nottingham"]
-    text = ga.search_task_text(engines(c["fc"], c["fs"]), str(f))
-    got_runs, tail = parse_stdout(text)
+    acq = engines(c["fc"], c["fs"])
+    ref_all = np.load(FULL_PEAKS)
+    assert len(ref_all) == 340 * 32 and int((ref_all["snr"] >= 25).sum()) == 3582          # SURVEY App. B.3
+    for label, data, runs in _capture_slices():
+        got = acq.search_blocks(data)
+        ref = np.concatenate([ref_all[r * 32:(r + 1) * 32] for r in runs])
+        assert len(got) == len(ref)
+        worst = compare_peaks(got, ref)
+        print(f"whole-capture peaks [{label}]: {len(got)} chunks, {int((ref['snr'] >= 25).sum())} reference hits, worst SNR rel err {worst:.2e}")
+
+
+def test_marginal_hits_vs_reference(engines):
+    """The 103 chunks of the capture whose reference SNR lies in [24, 26] -- every hit and miss hugging the
+    SNR-25 threshold (24 hits within +-0.5) -- searched for their own PRN: SNR within 1e-4,
+    the same cell wins, and the detection decision agrees outside the 1e-3 band around 25."""
+    c = CAPTURES["nottingham"]
+    meta = json.loads((GOLD / "nottingham_marginal_chunks.json").read_text())
+    data = (GOLD / "nottingham_marginal_chunks.bin").read_bytes()
+    idx, sv = np.array(meta["chunk"]), np.array(meta["sv"], np.int32)
+    ref = np.load(FULL_PEAKS)[idx]
+    assert len(idx) >= 100 and int((np.abs(ref["snr"] - 25) <= 0.5).sum()) >= 24
+    got = engines(c["fc"], c["fs"]).search_blocks(data, sv)
+    rel = np.abs(got["snr"].astype(np.float64) / ref["snr"] - 1)
+    assert rel.max() <= SNR_RTOL, rel.max()
+    assert np.array_equal(got["lo_shift"], ref["lo_shift"]) and np.array_equal(got["ca_shift"], ref["ca_shift"])
+    decided = np.abs(ref["snr"] / 25.0 - 1) > 1e-3
+    assert np.array_equal((got["snr"] >= 25)[decided], (ref["snr"] >= 25)[decided])
+    assert np.array_equal(got["flags"] & 1, (got["snr"] >= 25).astype(np.int32))
+
+
+def test_whole_capture_search_task_text(ga, engines):
+    """SearchTask()'s printed report (Python mirror over the C ABI) against the reference's stdout."""
+    c = CAPTURES["nottingham"]
     ref_runs, _ = parse_stdout(strip_banner(c["stdout"].read_text()))
-    assert len(got_runs) == 340 and tail == ["run out of file!"]
-    compare_runs(got_runs, ref_runs)
+    assert len(ref_runs) == 340
+    for label, data, runs in _capture_slices():
+        f = FULL_CAPTURE if label == "full" else STRIDED
+        text = ga.search_task_text(engines(c["fc"], c["fs"]), str(f))
+        got_runs, tail = parse_stdout(text)
+        assert tail == ["run out of file!"] and len(got_runs) == len(runs)
+        compare_runs(_renumber(got_runs, runs), [ref_runs[r] for r in runs])
+
+
+def test_whole_capture_gps_test_binary():
+    """The C++ drop-in `gps_test` (reference CLI) over the whole capture / the strided runs."""
+    c = CAPTURES["nottingham"]
+    subprocess.run(["make", "-s", "gps_test"], cwd=ROOT, check=True)
+    ref_runs, _ = parse_stdout(strip_banner(c["stdout"].read_text()))
+    for label, data, runs in _capture_slices():
+        f = FULL_CAPTURE if label == "full" else STRIDED
+        r = subprocess.run([str(PKG / "c" / "gps_test"), str(f), repr(c["fc"]), repr(c["fs"]), "5000"],
+                           capture_output=True, text=True, timeout=600)
+        assert r.returncode == 0, r.stderr
+        got_runs, tail = parse_stdout(strip_banner(r.stdout))
+        assert tail == ["run out of file!"] and len(got_runs) == len(runs)
+        compare_runs(_renumber(got_runs, runs), [ref_runs[r] for r in runs])
 
 
 # ---- batching, ragged sizes, explicit PRN maps --------------------------------------------------------

@@ -89,6 +89,49 @@ def test_golden_stdout_is_complete():
     assert len(runs) == 12 and 7 in runs[0]["sv"]
 
 
+def test_full_capture_goldens_agree_with_each_other(ga):
+    """tests/golden/ref_peaks_nottingham_full.npy (the reference's Sample()+Correlate() returns for all 10,880 chunks,
+    made by make_golden_full.py) formatted like SearchTask() prints them reproduces the reference's own stdout
+    (nottingham_full.stdout.txt, made by gps_test_ref) over all 340 runs; the strided / marginal fixtures are the
+    slices of the capture their json files say."""
+    import json
+    from conftest import GOLD
+    pk = np.load(GOLD / "ref_peaks_nottingham_full.npy")
+    assert len(pk) == 340 * 32 and np.array_equal(pk["sv"], np.arange(len(pk)) % 32)
+    assert int((pk["snr"] >= 25).sum()) == 3582 and int((np.abs(pk["snr"] - 25) <= 0.5).sum()) >= 24      # SURVEY App. B.3
+    ref_runs, _ = parse_stdout(strip_banner(CAPTURES["nottingham"]["stdout"].read_text()))
+    full = np.zeros(len(pk), ga.PEAK_DTYPE)
+    for k in ("snr", "lo_shift", "ca_shift", "sv"):
+        full[k] = pk[k]
+    text = "".join(ga.format_run(r, full[32 * r: 32 * r + 32]) for r in range(340))
+    assert text == strip_banner(CAPTURES["nottingham"]["stdout"].read_text()).replace("run out of file!\n", "")
+    first = np.load(CAPTURES["nottingham"]["peaks"])             # made with the built-in FFT behind the shim, this one with MKL
+    assert all(np.array_equal(pk[k][:128], first[k]) for k in ("lo_shift", "ca_shift", "sv"))
+    assert np.abs(pk["snr"][:128] / first["snr"] - 1).max() < 2e-6
+    runs = json.loads((GOLD / "nottingham_strided_runs.json").read_text())["runs"]
+    assert (GOLD / "nottingham_strided_runs.bin").stat().st_size == len(runs) * 32 * 5120
+    m = json.loads((GOLD / "nottingham_marginal_chunks.json").read_text())
+    assert (GOLD / "nottingham_marginal_chunks.bin").stat().st_size == len(m["chunk"]) * 5120
+    assert np.all((pk["snr"][m["chunk"]] >= 24) & (pk["snr"][m["chunk"]] <= 26))
+    # the first strided run is run 100 of the capture: its first chunk is the one the marginal list may also hold
+    assert runs[:4] == [100, 101, 102, 103]
+
+
+def test_oracle_on_threshold_hugging_chunks(oracle_mod):
+    """The C restatement against the reference on chunks whose SNR hugs the threshold (a sample of the 103 with
+    reference SNR in [24, 26]): same cell, SNR within 2e-5."""
+    import json
+    from conftest import GOLD
+    m = json.loads((GOLD / "nottingham_marginal_chunks.json").read_text())
+    data = (GOLD / "nottingham_marginal_chunks.bin").read_bytes()
+    ref = np.load(GOLD / "ref_peaks_nottingham_full.npy")[m["chunk"]]
+    pick = np.argsort(np.abs(ref["snr"] - 25))[:12]                 # the 12 closest to 25
+    o = oracle_mod.Oracle(4.092e6, 5.456e6)
+    got = o.search_blocks(b"".join(data[i * 5120:(i + 1) * 5120] for i in pick), np.array(m["sv"], np.int32)[pick])
+    assert np.array_equal(got["lo_shift"], ref["lo_shift"][pick]) and np.array_equal(got["ca_shift"], ref["ca_shift"][pick])
+    assert np.abs(got["snr"] / ref["snr"][pick] - 1).max() < 2e-5
+
+
 def test_live_reference_agrees_with_oracle(oracle_mod):
     """When oracle/_ref was built here (or travelled prebuilt), drive the real reference TU."""
     if not oracle_mod.ref_available():
@@ -148,3 +191,32 @@ def test_grid_oracle_matches_numpy_definition(oracle_mod, ga, fs, fc, step, K):
         assert abs(r["snr"] / best[0] - 1) < 2e-5
         if best[0] >= 25:
             assert (int(r["lo_shift"]), int(r["ca_shift"])) == best[1:]
+
+
+# ---- GRID mode pinned to what the reference holds (CPU: the oracle's definition; the GPU twins are in test_gpu_grid.py) ----
+def test_grid_oracle_agrees_with_the_reference_on_the_capture(oracle_mod):
+    """Every detection of the UNMODIFIED reference in run 0 of the capture (10 SVs) is found by the GRID definition
+    (7 non-coherent 1 ms blocks of the same chunk, 500 Hz bins) at the reference's code phase (+-1 sample) and within
+    one bin of its Doppler -- SURVEY App. D's acceptance criterion for GRID vs REF."""
+    c = CAPTURES["nottingham"]
+    data = c["bin"].read_bytes()
+    ref = np.load(c["peaks"])[:32]
+    g = oracle_mod.GridOracle(c["fc"], c["fs"], 5000.0, 500.0, 7)
+    hits = np.nonzero(ref["snr"] >= 25)[0]
+    assert len(hits) == 10
+    for i in hits:
+        p = g.acquire(data[i * 5120: i * 5120 + 7 * 682], svs=[i % 32])[0]
+        d = abs(int(p["ca_shift"]) - int(ref[i]["ca_shift"]))
+        assert min(d, 5456 - d) <= 1 and abs(p["lo_shift"] * 500.0 - ref[i]["lo_shift"] * c["fs"] / 40000) <= 500.0
+
+
+def test_grid_oracle_vs_the_dataset_page_known_answer(oracle_mod):
+    """250 Hz bins on the first 20 ms of the capture: PRN 1/21/29/30/31 within +-1 bin of lo_shift 6/8/-9/-9/-8
+    ("Raw GPS signal samples data set for testing GPS receivers.html", Holme's search on this file)."""
+    c = CAPTURES["nottingham"]
+    known = {0: 6, 20: 8, 28: -9, 29: -9, 30: -8}
+    g = oracle_mod.GridOracle(c["fc"], c["fs"], 5000.0, 250.0, 10)
+    out = g.acquire(c["bin"].read_bytes()[: 2 * 6820], svs=sorted(known)).reshape(2, 5)
+    for a in range(2):
+        for n, sv in enumerate(sorted(known)):
+            assert out[a, n]["snr"] >= 25 and abs(int(out[a, n]["lo_shift"]) - known[sv]) <= 1
