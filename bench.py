@@ -10,20 +10,27 @@ semantics (N = 40000-point coherent window, 73 Doppler bins of fs/N = 136.4 Hz, 
 chunk per PRN; c/search_offline.cpp:176,239-246), because that is the only grid on which parity
 with gps_test is defined and the only one the reference arm can run.
 
-A "step" is one batch of 16 runs = 512 chunks x 73 bins = 37,376 correlations per GPU: forward
-FFT kernel, cell kernel (shifted conj-multiply + pruned backward FFT + |.|^2 + peak), best-over-
-Doppler kernel, and for N > 1 one NCCL all-gather of the 512 32-byte peak records per rank.
+A "step" is one batch of 224 runs = 7168 chunks x 73 bins = 523,264 correlations per GPU (~60 ms, so
+that 20 timed steps run for more than a second): forward FFT kernel, cell kernel (shifted conj-multiply
++ pruned backward FFT + |.|^2 + peak), best-over-Doppler kernel, and for N > 1 one NCCL all-gather of
+the 7168 32-byte peak records per rank -- inside the timed region of BOTH value and e2e.
 Ranks work on different runs of the stream (weak scaling, no data-path collective).
 
 value   : device-resident inputs (packed bits already in HBM), CUDA events on the launching stream.
 e2e     : same step through the host-buffer C-ABI call gpsacq_search_blocks(): pinned host bits ->
-          H2D -> kernels -> D2H peak records, host synchronised, every step.
+          H2D -> kernels -> D2H peak records, host synchronised, every step; for N > 1 followed by the
+          all-gather of every rank's records and their read-back to the host.
 roofline: the cell kernel alone.  achieved = 640,016 algorithmic bytes per correlation (one read
           of the 40000-point complex64 block spectrum + one of the replica spectrum + a 16-byte
           record) x correlations per launch / average launch time from CUDA
           events recorded around the launch inside libgpsacq (gpsacq_stage_times()).
           peak = MEASURED_PEAKS.json hbm_gbs.  The operands are L2-resident after first touch, so
-          the real DRAM traffic is far below the algorithmic bytes (roofline.traffic, from ncu).
+          the real DRAM traffic is far below the algorithmic bytes (roofline.traffic, from ncu) and the
+          kernel is bound by FP32 issue: roofline.fp32_frac = executed FP32 flops (ncu instruction counts
+          per correlation, profiles/cell_kernel_ncu.json) / live launch time / 74.4 TFLOP/s, next to the
+          ncu issue-slot and FMA-pipe utilisation of the same capture.
+Secondary blocks in the same line (N = 1): GRID-mode throughput for BASELINE.json configs[1], [2], [3]
+(grid_mode_configs1/2/3) and the Doppler-sharded configs[4] acquisition (grid_mode_configs4_sharded).
 """
 import argparse
 import json
@@ -42,30 +49,45 @@ ROOT = Path(__file__).resolve().parent
 sys.path.insert(0, str(ROOT))
 
 FC, FS, MAX_FO = 4.092e6, 5.456e6, 5000.0
-RUNS_PER_STEP = 16
+RUNS_PER_STEP = 224                  # 7168 chunks x 73 bins = 523,264 correlations (~60 ms) per GPU per step
 CHUNK = 5120
 N_BATCHES = 4                       # distinct input batches cycled through the steps
+FP32_PEAK_TFLOPS = 74.4             # 148 SMs x 128 FP32 lanes x 2 flops x 1.965 GHz (non-tensor FP32 peak of a B200)
 METRIC = "PRN×Doppler correlations/sec"
 UNIT = "correlations/s"
 
 
-def make_batches(n_batches: int, seed: int):
+def bench_sats():
     import gpsacq_loader
     import importlib
     gpsacq_loader.load()
     sg = importlib.import_module("gnss_gps_sdr_b200.siggen")
-    sats = sg.default_constellation(FS, seed=1575420000)
+    return sg, sg.default_constellation(FS, seed=1575420000)
+
+
+def make_batches(n_batches: int, seed: int, device: int):
+    """Synthetic captures of the bench workload (8 satellites at 45 dB-Hz + noise), made on the GPU by the library's
+    own generator (gpsacq_synth_capture; the numpy generator would need minutes for 4 x 294 M samples)."""
+    import gpsacq_loader
+    ga = gpsacq_loader.load()
+    _, sats = bench_sats()
     n_samples = RUNS_PER_STEP * 32 * CHUNK * 8
-    return [sg.synth_capture(n_samples, FS, FC, sats, seed=seed * 1000 + b) for b in range(n_batches)]
+    return [ga.synth_capture_gpu(n_samples, FS, FC, sats, seed=seed * 1000 + b, device=device) for b in range(n_batches)]
+
+
+def make_cpu_sample(runs: int, seed: int):
+    """The same workload for the CPU legs (numpy generator: no GPU needed by the reference arm)."""
+    sg, sats = bench_sats()
+    return sg.synth_capture(runs * 32 * CHUNK * 8, FS, FC, sats, seed=seed)
 
 
 def workload_config(n_gpus: int):
     return {"workload": "C1-REF: synthetic 1-bit IF fs=5.456MHz if=4.092MHz, 32 PRN x 73 Doppler bins "
-                        "(+-5 kHz @ 136.4 Hz), N=40000 coherent (7.33 ms), 16 runs (512 chunks) per GPU per step",
+                        f"(+-5 kHz @ 136.4 Hz), N=40000 coherent (7.33 ms), {RUNS_PER_STEP} runs ({RUNS_PER_STEP * 32} chunks) per GPU per step",
             "correlations_per_step_per_gpu": RUNS_PER_STEP * 32 * 73,
-            "sharding": f"runs of the stream split over {n_gpus} GPU(s); NCCL all-gather of peak records, overlapped with the next step (double-buffered records)"
+            "sharding": f"runs of the stream split over {n_gpus} GPU(s); NCCL all-gather of peak records every step, overlapped with the next step's kernels (double-buffered records)"
                         if n_gpus > 1 else "single GPU",
-            "l2_policy": "inputs larger than L2: each step's cell-kernel operands are 164 MB of block spectra "
+            "l2_policy": f"inputs larger than L2: each step's cell-kernel operands are {RUNS_PER_STEP * 32 * 320 // 1000} MB of block spectra "
                          "+ 20 MB of replica spectra (> 126 MB L2); 4 distinct input batches are cycled"}
 
 
@@ -160,7 +182,7 @@ def cpu_sample_file() -> str:
     global _CPU_SAMPLE
     if _CPU_SAMPLE is None:
         with tempfile.NamedTemporaryFile(suffix=".bin", delete=False) as f:
-            make_batches(1, seed=77)[0].tofile(f)
+            make_cpu_sample(16, seed=77).tofile(f)
             _CPU_SAMPLE = f.name
     return _CPU_SAMPLE
 
@@ -230,7 +252,7 @@ def run_engine(args, rank, world, local_rank):
     torch.cuda.set_device(dev)
 
     nb = RUNS_PER_STEP * 32
-    batches = make_batches(N_BATCHES, seed=rank + 1)            # every rank searches different runs of the stream
+    batches = make_batches(N_BATCHES, seed=rank + 1, device=local_rank)   # every rank searches different runs of the stream
     acq = ga.Acquisition(FC, FS, MAX_FO, device=local_rank, max_blocks=nb)
     ndop = acq.n_doppler
     corr_per_step = nb * ndop
@@ -290,14 +312,29 @@ def run_engine(args, rank, world, local_rank):
     stage = acq.stage_times()
 
     # ---- end to end through the host-buffer C-ABI call --------------------------------------------
+    # every step: pinned host bits -> gpsacq_search_blocks() (H2D, kernels, D2H, host sync) -> records on the host;
+    # N > 1: followed by the peak gather (records back to the device buffer NCCL reads, all-gather, read-back of all
+    # ranks' records), so that the exchange is inside this timed region too
     acq.set_stream(None)
+    torch.cuda.set_stream(torch.cuda.default_stream(dev))
+    h_all = torch.zeros(world * nb * 32, dtype=torch.uint8).pin_memory() if world > 1 else None
+
+    def step_e2e(i):
+        pk = acq.search_blocks(h_bits[i % N_BATCHES].numpy())
+        if world > 1:
+            d_outs[0].copy_(torch.from_numpy(pk.view(np.uint8).reshape(-1)), non_blocking=True)
+            dist.all_gather_into_tensor(d_alls[0], d_outs[0])
+            h_all.copy_(d_alls[0], non_blocking=True)
+            torch.cuda.current_stream(dev).synchronize()
+        return pk
+
     peaks = None
     for i in range(min(args.warmup, 3)):
-        peaks = acq.search_blocks(h_bits[i % N_BATCHES].numpy())
+        peaks = step_e2e(i)
     barrier()
     t0 = time.perf_counter()
     for i in range(args.steps):
-        peaks = acq.search_blocks(h_bits[i % N_BATCHES].numpy())
+        peaks = step_e2e(i)
     torch.cuda.synchronize(dev)
     e2e_s = time.perf_counter() - t0
 
@@ -317,10 +354,15 @@ def run_engine(args, rank, world, local_rank):
         bpc = acq.info["bytes_per_corr"]
         cell_avg_ms = statistics.mean(cell_ms)
         achieved = corr_per_step * bpc / (cell_avg_ms * 1e-3) / 1e9
-        traffic = None
-        prof = ROOT / "profiles" / "cell_kernel_dram.json"
+        # ncu-derived per-correlation figures of the same kernel (profiles/cell_kernel_ncu.json, made by tools/ncu_summary.py
+        # + tools/ncu_flops.py from the committed capture): DRAM bytes, executed FP32 flops, issue-slot / FMA-pipe utilisation
+        traffic = fp32 = None
+        ncu = {}
+        prof = ROOT / "profiles" / "cell_kernel_ncu.json"
         if prof.exists():
-            traffic = json.loads(prof.read_text()).get("dram_bytes_per_launch")
+            ncu = json.loads(prof.read_text())
+            traffic = ncu["dram_bytes_per_corr"] * corr_per_step
+            fp32 = ncu["fp32_flops_per_corr"] * corr_per_step / (cell_avg_ms * 1e-3) / 1e12
         value = world * corr_per_step * args.steps / (total_ms * 1e-3)
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True,
@@ -329,7 +371,11 @@ def run_engine(args, rank, world, local_rank):
                 "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak_gbs, "unit": "GB/s",
                              "frac": achieved / peak_gbs, "traffic": traffic, "kernel": "cell_kernel",
                              "launch_ms": cell_avg_ms, "bytes_per_launch": corr_per_step * bpc, "peak_source": peak_src,
-                             "whole_step_frac": value / world * bpc / 1e9 / peak_gbs},
+                             "whole_step_frac": value / world * bpc / 1e9 / peak_gbs,
+                             "fp32_tflops": fp32, "fp32_peak_tflops": FP32_PEAK_TFLOPS,
+                             "fp32_frac": None if fp32 is None else fp32 / FP32_PEAK_TFLOPS,
+                             "issue_active_pct_ncu": ncu.get("issue_active_pct"), "fma_pipe_active_pct_ncu": ncu.get("fma_pipe_active_pct"),
+                             "ncu_capture": ncu.get("source")},
                 "e2e": {"value": world * corr_per_step * args.steps / (e2e_ms * 1e-3), "unit": UNIT,
                         "h2d_bytes_per_step": nb * CHUNK + nb * 4, "d2h_bytes_per_step": nb * 32,
                         "ms_per_step": e2e_ms / args.steps},
@@ -342,7 +388,8 @@ def run_engine(args, rank, world, local_rank):
             grid_c4["frac_of_hbm_peak_per_gpu"] = grid_c4["contract_gbs"] / world / peak_gbs
             line["grid_mode_configs4_sharded"] = grid_c4
         if world == 1 and not args.no_grid:
-            line["grid_mode_configs1"] = grid_c1_measure(ga, dev, peak_gbs)
+            for name in ("configs1", "configs2", "configs3"):
+                line["grid_mode_" + name] = grid_measure(ga, dev, peak_gbs, name)
         if world == 1 and not args.no_cpu_baseline:
             cb, _, _ = cpu_baseline(runs_per_core=4)
             os.unlink(cpu_sample_file())
@@ -414,38 +461,56 @@ def grid_c4_sharded(ga, dev, rank, world, dist):
     return out
 
 
-def grid_c1_measure(ga, dev, peak_gbs):
-    """Secondary, informational: BASELINE.json configs[1] in GRID semantics (1 ms coherent, +-5 kHz @ 500 Hz,
-    21 bins, all 32 PRNs on the same block) -- a mode the reference does not have (no reference arm, parity
-    against the oracle's definition only).  192 acquisitions per launch (operands > L2), device-resident, CUDA events."""
+GRID_CONFIGS = {
+    # BASELINE.json configs[1..3] in GRID semantics: n_acq acquisitions per launch, sized so that the
+    # block spectra of a launch exceed the 126 MB L2 where the shape allows it
+    "configs1": dict(fs=5.456e6, fc=4.092e6, max_fo=5000.0, step=500.0, K=1, n_acq=192, seed=1575420000,
+                     what="fs=5.456MHz, 32 PRN x 21 bins (+-5 kHz @ 500 Hz), 1 ms coherent"),
+    "configs2": dict(fs=8.184e6, fc=2.046e6, max_fo=5000.0, step=500.0, K=1, n_acq=128, seed=1575420000,
+                     what="fs=8.184MHz (gps_sig_gen.m rate), 32 PRN x 21 bins (+-5 kHz @ 500 Hz), 1 ms coherent"),
+    "configs3": dict(fs=2.8e6, fc=0.62e6, max_fo=100000.0, step=250.0, K=10, n_acq=4, seed=1575420001,
+                     what="fs=2.8MHz (rtl-sdr rate), 32 PRN x 801 bins (+-100 kHz @ 250 Hz), 10 ms non-coherent"),
+}
+
+
+def grid_measure(ga, dev, peak_gbs, name):
+    """Secondary: one BASELINE.json config in GRID semantics (1 ms coherent blocks, explicit Doppler grid, K-block
+    non-coherent sums, all 32 PRNs on the same blocks) -- a mode the reference does not have (no reference arm; parity
+    against the oracle's definition and the reference-held vectors, tests/test_gpu_grid.py).  Device-resident input,
+    CUDA events on the launching stream; contract bytes 2*W*8+16 per coherent correlation."""
     import importlib
     import torch
     sg = importlib.import_module("gnss_gps_sdr_b200.siggen")
-    n_acq, W = 192, 5456          # 192 x 21 block spectra = 176 MB > 126 MB L2
-    bits = sg.synth_capture(W * n_acq, FS, FC, sg.default_constellation(FS, seed=1575420000), seed=3)
-    acq = ga.Acquisition(FC, FS, MAX_FO, device=dev.index, mode=1, doppler_step=500.0, noncoh_blocks=1, max_blocks=n_acq)
+    c = GRID_CONFIGS[name]
+    W = int(round(c["fs"] / 1000))
+    sats = sg.default_constellation(c["fs"], seed=c["seed"], max_doppler=0.9 * c["max_fo"])
+    acq = ga.Acquisition(c["fc"], c["fs"], c["max_fo"], device=dev.index, mode=1, doppler_step=c["step"], noncoh_blocks=c["K"],
+                         max_blocks=c["n_acq"])
+    n_acq = min(c["n_acq"], acq.info["max_acq"])
+    bits = ga.synth_capture_gpu(W * c["K"] * n_acq, c["fs"], c["fc"], sats, seed=3, device=dev.index)
     d_bits = torch.from_numpy(bits).to(dev)
     d_out = torch.zeros(n_acq * 32 * 32, dtype=torch.uint8, device=dev)
     stream = torch.cuda.current_stream(dev)
     acq.set_stream(stream.cuda_stream)
     for _ in range(3):
         acq.acquire_device(d_bits.data_ptr(), n_acq, d_out.data_ptr())
+    reps = 20 if c["K"] == 1 else 5
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(stream)
-    for _ in range(20):
+    for _ in range(reps):
         acq.acquire_device(d_bits.data_ptr(), n_acq, d_out.data_ptr())
     e1.record(stream)
     torch.cuda.synchronize(dev)
-    ms = e0.elapsed_time(e1) / 20
-    corr = n_acq * 32 * acq.n_doppler
+    ms = e0.elapsed_time(e1) / reps
+    corr = n_acq * 32 * acq.n_doppler * c["K"]
     bpc = acq.info["bytes_per_corr"]
     native = acq.info["fft_len"] == W
-    out = {"workload": f"GRID C1: fs=5.456MHz, 32 PRN x 21 bins (+-5 kHz @ 500 Hz), 1 ms coherent, {n_acq} acquisitions per launch",
+    out = {"workload": f"GRID {name}: {c['what']}, {n_acq} acquisitions per launch",
            "value": corr / ms * 1e3, "unit": UNIT, "ms_per_launch": ms, "bytes_per_corr": bpc,
            "contract_gbs": corr * bpc / ms / 1e6, "frac_of_hbm_peak": corr * bpc / ms / 1e6 / peak_gbs,
            "stage_ms": {k: round(v, 4) for k, v in acq.stage_times().items()},
-           "note": ("native 5456-point prime-factor transform 16x11x31 (DESIGN.md section 10)" if native else
-                    "zero-padded embedding of the 5456-point correlation (DESIGN.md section 10)")}
+           "note": (f"native {W}-point prime-factor transform (DESIGN.md section 10)" if native else
+                    f"zero-padded embedding of the {W}-point correlation (DESIGN.md section 10)")}
     acq.close()
     return out
 

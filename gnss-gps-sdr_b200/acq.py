@@ -27,7 +27,8 @@ class _Cfg(C.Structure):
     _fields_ = [("fc", C.c_double), ("fs", C.c_double), ("max_fo", C.c_double),
                 ("fft_len", C.c_int32), ("device", C.c_int32), ("max_blocks", C.c_int32),
                 ("mode", C.c_int32), ("doppler_step", C.c_double), ("noncoh_blocks", C.c_int32),
-                ("dop_first", C.c_int32), ("dop_count", C.c_int32), ("reserved", C.c_int32)]
+                ("dop_first", C.c_int32), ("dop_count", C.c_int32), ("reserved", C.c_int32),
+                ("fs_replica", C.c_double)]
 
 
 class _Info(C.Structure):

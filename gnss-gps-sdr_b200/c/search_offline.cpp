@@ -38,6 +38,10 @@ bool g_busy[NUM_SATS];
 gpsacq_group_t *g_group = NULL;           // one engine per GPU + the peak-record gather (NCCL or host)
 int g_chunk_bytes = 0;
 int g_runs_per_batch = 16;
+// The reference reads FS in SearchInit() for the replicas (:76) and FC / FS / max_fo again on every Sample() and
+// Correlate() (:127,:176,:190).  The engine bakes them into device tables, so they are remembered here and the engine
+// is rebuilt when SearchTask() finds the globals changed (replicas stay at the SearchInit()-time FS, like there).
+double g_fs_init = 0, g_fc_used = 0, g_fs_used = 0, g_maxfo_used = 0;
 
 int env_int(const char *name, int dflt)
 {
@@ -64,9 +68,10 @@ void print_run(int run_count, const gpsacq_peak *pk)
 
 }  // namespace
 
-int SearchInit()
+static int build_engine(double fs_replica)
 {
-    SearchFree();
+    if (g_group) gpsacq_group_destroy(g_group);
+    g_group = NULL;
     const int first = env_int("GPSACQ_DEVICE", 0);
     int ngpu = env_int("GPSACQ_GPUS", 1);
     if (ngpu < 1) ngpu = 1;
@@ -76,6 +81,7 @@ int SearchInit()
     gpsacq_cfg cfg;
     memset(&cfg, 0, sizeof cfg);
     cfg.fc = FC; cfg.fs = FS; cfg.max_fo = max_fo;
+    cfg.fs_replica = fs_replica;
     cfg.fft_len = FFT_LEN;
     cfg.mode = GPSACQ_MODE_REF;
     cfg.max_blocks = g_runs_per_batch * NUM_SATS;      // per GPU
@@ -91,7 +97,14 @@ int SearchInit()
     gpsacq_info info;
     gpsacq_get_info(gpsacq_group_engine(g_group, 0), &info);
     g_chunk_bytes = info.chunk_bytes;
+    g_fc_used = FC; g_fs_used = FS; g_maxfo_used = max_fo;
     return 0;
+}
+
+int SearchInit()
+{
+    g_fs_init = FS;
+    return build_engine(0.0);
 }
 
 void SearchFree()
@@ -121,6 +134,10 @@ void SearchTask(char *filename_1bit_bin)
     FILE *fp = fopen(filename_1bit_bin, "rb");
     if (!fp) { printf("can not open file!\n"); return; }
     if (!g_group) { fclose(fp); fprintf(stderr, "SearchTask: SearchInit() has not succeeded\n"); return; }
+    if (FC != g_fc_used || FS != g_fs_used || max_fo != g_maxfo_used) {      // globals changed since the engine was built
+        const int rc = build_engine(g_fs_init);
+        if (rc) { fclose(fp); fprintf(stderr, "SearchTask: engine rebuild for changed FC/FS/max_fo failed (%d)\n", rc); return; }
+    }
 
     const size_t run_bytes = (size_t)NUM_SATS * g_chunk_bytes;
     std::vector<unsigned char> buf(run_bytes * g_runs_per_batch);

@@ -137,8 +137,8 @@ __global__ void __launch_bounds__(T, MODE == 0 ? FWD_MINB : 1) fwd_kernel(const 
     }
 }
 
-// (the register-accumulator, software-pipelined and rotating-layout variants of the hot kernel -- measured, slower, kept
-// behind macros -- live in ga_experiments.cuh)
+// (the register-accumulator, software-pipelined and rotating-layout variants of the hot kernel -- measured, slower --
+// are not part of the product: tools/experiments/ga_experiments.cuh)
 
 // ---------------------------------------------------------------------------------
 // Tensor-memory variant of the hot kernel: the per-thread output accumulators (NW complex
@@ -269,7 +269,7 @@ __global__ void __launch_bounds__(T, cell_minb(T)) cell_kernel_tm(const cf *__re
 
     for (int cell = blockIdx.x; cell < n_cells; cell += gridDim.x) {
         const int blk = cell / n_dop, dop = cell - blk * n_dop - dmax;
-        const int sv = sv_of_block ? sv_of_block[blk] : (blk & 31);
+        const int sv = (sv_of_block ? sv_of_block[blk] : blk) & 31;     // caller-supplied device maps are not trusted: see best_kernel
         const cf *xb = xd + (size_t)blk * G::N;
         const cf *cb = cext + (size_t)sv * (2 * G::N);
         float best = 0.0f, sum = 0.0f;
@@ -422,6 +422,7 @@ __global__ void best_kernel(const CellStat *__restrict__ cells, const int *__res
         }
         p.sv = sv_of_block ? sv_of_block[blk] : (blk & 31);
         p.flags = (snr < 25.0f) ? 0 : 1;
+        if (p.sv < 0 || p.sv > 31) p.flags |= (int)0x80000000u;    // device-side PRN map entry out of range: searched as sv & 31
         p.reserved = 0;
         peaks[blk] = p;
     }
@@ -440,4 +441,3 @@ __global__ void undecimate_kernel(const cf *__restrict__ in, int n1, int n2, int
 
 }  // namespace ga
 
-#include "ga_experiments.cuh"

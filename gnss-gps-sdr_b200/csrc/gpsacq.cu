@@ -9,6 +9,7 @@
 #include <stdlib.h>
 #include <string.h>
 #include <math.h>
+#include <cmath>
 #include <vector>
 #include <string>
 #include <algorithm>
@@ -33,10 +34,7 @@ static_assert(sizeof(gpsacq_cell) == sizeof(CellStat) && sizeof(gpsacq_cell) == 
 
 // ---- geometries: N = 40000 = N1 * (RA*RB*RC), N2 >= W --------------------------------
 typedef Geom<10, 20, 20, 10> G4000;    // W <= 4000   (FS <= 4 MHz, e.g. rtl-sdr 2.8 MHz)
-#ifndef GA_G8000_ROT
-#define GA_G8000_ROT 0
-#endif
-typedef Geom<5, 20, 20, 20, GA_G8000_ROT != 0> G8000;  // W <= 8000 (FS <= 8 MHz, e.g. 5.456 MHz); rotating smem layouts
+typedef Geom<5, 20, 20, 20> G8000;     // W <= 8000   (FS <= 8 MHz, e.g. 5.456 MHz)
 typedef Geom<4, 25, 20, 20> G10000;    // W <= 10000  (FS <= 10 MHz, e.g. 8.184 MHz, 10 MHz)
 enum { GID_4000 = 0, GID_8000 = 1, GID_10000 = 2 };
 // GRID mode: L = 2*N2 >= 2W (linear-correlation embedding of the W-point circular correlation)
@@ -125,6 +123,14 @@ static const unsigned char kTaps[32][2] = {
 
 static thread_local std::string g_create_error;
 
+// Every entry point that selects a device restores the caller's current device on return: a host application
+// (torch, another CUDA library on the same thread) keeps launching where it was.
+struct DeviceGuard {
+    int prev;
+    DeviceGuard() : prev(-1) { if (cudaGetDevice(&prev) != cudaSuccess) prev = -1; }
+    ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+
 struct gpsacq {
     gpsacq_cfg cfg;
     int gid, n, n1, n2, w, dmax, ndop, chunk_bytes, chunk_samples, cap, device, sm_count;
@@ -170,27 +176,10 @@ struct gpsacq {
     } while (0)
 
 // ---- kernel dispatch ------------------------------------------------------------------
-#ifndef CELL_MAXREG
-#define CELL_MAXREG 144      // 2 CTAs x 7 warps x 32 lanes x 144 regs <= 64K registers per SM
-#endif
-
-#ifndef GA_CELL_PIPE
-#define GA_CELL_PIPE 0       // (experiment, slower: spills) prefetch the next sub-sequence's operands behind the barriers (cell_kernel_tm2)
-#endif
-#ifndef GA_CELL_TMEM
-#define GA_CELL_TMEM 1       // accumulators in tensor memory (cell_kernel_tm); 0 = registers (cell_kernel)
-#endif
-
+// (the measured-and-slower variants of the hot kernel -- register accumulators, software-pipelined operand prefetch,
+// rotating shared-memory layouts -- are kept outside the product under tools/experiments/)
 template <class G, int T, int NW, int GID> struct CellKernel {
-    static auto get()
-    {
-        if constexpr (G::ROT) return cell_kernel_rot<G, T, NW, CELL_MAXREG, GID>;   // experimental 2-barrier kernel
-        else if constexpr (GA_CELL_TMEM != 0 && GA_CELL_PIPE != 0 && T % 32 == 0 && G::RA == 20 && G::NA == G::NB &&
-                           G::NB == G::NC && cdiv(G::NA, 32) <= T / 32 && 2 * NW <= 32)
-            return cell_kernel_tm2<G, T, NW, GID>;       // software-pipelined operand prefetch
-        else if constexpr (GA_CELL_TMEM != 0 && T % 32 == 0) return cell_kernel_tm<G, T, NW, GID>;
-        else return cell_kernel<G, T, NW, CELL_MINB, GID>;
-    }
+    static auto get() { return cell_kernel_tm<G, T, NW, GID>; }
 };
 
 template <class G, int T, int NW, int GID>
@@ -226,7 +215,7 @@ static int setup_cells_t(gpsacq *h)
     // column count, a run-time operand of tcgen05.alloc, and reports one CTA per SM).  Registers and
     // shared memory are sized for cell_minb(T) CTAs (__launch_bounds__, carveout above) and each CTA
     // allocates at most 512 / cell_minb(T) TMEM columns, so that many CTAs are resident.
-    if (GA_CELL_TMEM != 0 && !G::ROT && T % 32 == 0 && per_sm < MINB) per_sm = MINB;
+    if (per_sm < MINB) per_sm = MINB;
     h->cell_ctas = per_sm * h->sm_count;
     return 0;
 }
@@ -235,16 +224,28 @@ template <class G, int MODE, int GID>
 static int launch_fwd_t(gpsacq *h, size_t n_items, const unsigned char *d_bits, cf *out)
 {
     auto kern = fwd_kernel<G, FWD_T, MODE, GID>;
-    const int smem = (int)(G::SMEM_ELEMS * sizeof(cf));
-    CUDA_TRY(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    const int smem = (int)(G::SMEM_ELEMS * sizeof(cf));       // opted in once by setup_fwd_t()
     kern<<<(unsigned)(n_items * G::N1), FWD_T, smem, h->stream>>>(d_bits, h->chunk_bytes, h->d_lo, h->d_repl_time,
                                                                   h->d_tw, out);
     CUDA_TRY(h, cudaGetLastError());
     return 0;
 }
 
+template <class G, int GID> static int setup_fwd_t(gpsacq *h)
+{
+    const int smem = (int)(G::SMEM_ELEMS * sizeof(cf));
+    CUDA_TRY(h, cudaFuncSetAttribute(fwd_kernel<G, FWD_T, 0, GID>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    CUDA_TRY(h, cudaFuncSetAttribute(fwd_kernel<G, FWD_T, 1, GID>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    return 0;
+}
+
 static int setup_cells(gpsacq *h)
 {
+    {
+        const int rc = h->gid == GID_4000 ? setup_fwd_t<G4000, GID_4000>(h)
+                     : h->gid == GID_8000 ? setup_fwd_t<G8000, GID_8000>(h) : setup_fwd_t<G10000, GID_10000>(h);
+        if (rc) return rc;
+    }
     switch (h->gid) {
     case GID_4000:
         return h->w <= 7 * G4000::OUT_STRIDE ? setup_cells_t<G4000, CELL_T_4000, 7, GID_4000>(h)
@@ -378,6 +379,9 @@ static int create_impl(gpsacq *h)
     if (!(c.fs > 0) || !(c.fc >= 0) || !(c.max_fo >= 0)) { h->err = "fc, fs, max_fo must be positive"; return GPSACQ_EINVAL; }
     h->n = c.fft_len ? c.fft_len : GPSACQ_FFT_LEN;
     if (h->n != GPSACQ_FFT_LEN) { h->err = "only fft_len = 40000 (FFT_LEN, c/gps_offline.h:15) is supported"; return GPSACQ_EINVAL; }
+    if (!(c.fs / 1000.0 <= (double)h->n) || !(c.max_fo * (double)h->n / c.fs < (double)(1 << 24))) {
+        h->err = "FS/1000 must not exceed fft_len and max_fo*fft_len/FS must be a sane bin count"; return GPSACQ_EINVAL;
+    }
     h->w = (int)ceil(c.fs / 1000.0);                          // for (i=0; i<FS/1000; i++)  (:190)
     h->dmax = (int)(c.max_fo * (double)h->n / c.fs);          // C truncation, (:176)
     h->ndop = 2 * h->dmax + 1;
@@ -420,7 +424,7 @@ static int create_impl(gpsacq *h)
     build_lo_table(c.fc, c.fs, h->chunk_samples, lo);
     CUDA_TRY(h, cudaMemcpy(h->d_lo, lo.data(), lo.size(), cudaMemcpyHostToDevice));
     std::vector<unsigned short> ci; std::vector<float> ba, bb;
-    build_code_nco(c.fs, h->n, ci, ba, bb);
+    build_code_nco(c.fs_replica > 0 ? c.fs_replica : c.fs, h->n, ci, ba, bb);     // SearchInit()-time FS (:76)
     CUDA_TRY(h, cudaMemcpy(h->d_chip_idx, ci.data(), n * sizeof(unsigned short), cudaMemcpyHostToDevice));
     CUDA_TRY(h, cudaMemcpy(h->d_blend_a, ba.data(), n * sizeof(float), cudaMemcpyHostToDevice));
     CUDA_TRY(h, cudaMemcpy(h->d_blend_b, bb.data(), n * sizeof(float), cudaMemcpyHostToDevice));
@@ -457,6 +461,7 @@ template <class H, int T, int NW, int HID> struct GridOps {
         h->cell_ctas = CELL_MINB * h->sm_count;      // TMEM kernels: see setup_cells_t
         auto fk = fwd_grid_kernel<H, FWD_T, HID>;
         CUDA_TRY(h, cudaFuncSetAttribute(fk, cudaFuncAttributeMaxDynamicSharedMemorySize, h->cell_smem));
+        CUDA_TRY(h, cudaFuncSetAttribute(fwd_kernel<H, FWD_T, 1, HID>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->cell_smem));
         return 0;
     }
     static int fwd_blocks(gpsacq *h, size_t n_blocks, const unsigned char *d_bits)
@@ -571,6 +576,9 @@ static int create_grid(gpsacq *h)
     const gpsacq_cfg &c = h->cfg;
     if (!(c.fs > 0) || !(c.fc >= 0) || !(c.max_fo >= 0) || !(c.doppler_step > 0)) { h->err = "GRID mode needs fs, doppler_step > 0"; return GPSACQ_EINVAL; }
     const double wd = c.fs / 1000.0, md = c.fs / c.doppler_step;
+    if (!(wd < 1e6) || !(md < (double)(1 << 28)) || !(c.max_fo / c.doppler_step < (double)(1 << 24))) {
+        h->err = "GRID mode: FS/1000, FS/doppler_step or max_fo/doppler_step out of range"; return GPSACQ_EINVAL;
+    }
     h->w = (int)llround(wd);
     h->wipe_m = (int)llround(md);
     if (fabs(wd - h->w) > 1e-9 || h->w % 8) { h->err = "GRID mode needs FS/1000 to be an integer multiple of 8 samples"; return GPSACQ_EINVAL; }
@@ -609,12 +617,14 @@ static int create_grid(gpsacq *h)
     { const int rc_dev = open_device(h); if (rc_dev) return rc_dev; }
 
     // Doppler bins R = 1000/step apart differ by exactly one DFT bin of the 1 ms block (M = R*W): the native path
-    // transforms only the bins 0..R-1 of each block and rotates (GPSACQ_GRID_NOSHARE=1 turns this off, for A/B runs)
+    // transforms only the bins 0..R-1 of each block and rotates (GPSACQ_GRID_NOSHARE=1 turns this off, for A/B runs).
+    // Decided from the FULL grid, not from this handle's shard: a shard of <= R bins must use the same arithmetic as
+    // the unsharded handle, or near-tie winners could differ between a sharded and an unsharded search.
     h->n_base = 0;
     {
         const char *ns = getenv("GPSACQ_GRID_NOSHARE");
         const int r = h->w > 0 ? h->wipe_m / h->w : 0;
-        if ((h->gid >= PID_5456 || h->n1 == 1) && !(ns && *ns && *ns != '0') && r >= 1 && (long long)r * h->w == h->wipe_m && r < h->ndop) h->n_base = r;
+        if ((h->gid >= PID_5456 || h->n1 == 1) && !(ns && *ns && *ns != '0') && r >= 1 && (long long)r * h->w == h->wipe_m && r < ndop_full) h->n_base = r;
     }
     // batch capacity: keep the block spectra of one batch under ~3 GB
     const size_t per_acq = (size_t)h->kblocks * (h->n_base > 0 ? h->n_base : h->ndop) * h->n * sizeof(cf);
@@ -709,6 +719,7 @@ extern "C" {
 
 int gpsacq_create(const gpsacq_cfg *cfg, gpsacq_t **out)
 {
+    DeviceGuard guard;
     if (!cfg || !out) { g_create_error = "null argument"; return GPSACQ_EINVAL; }
     *out = nullptr;
     gpsacq *h = new (std::nothrow) gpsacq();
@@ -729,6 +740,7 @@ int gpsacq_create(const gpsacq_cfg *cfg, gpsacq_t **out)
 
 void gpsacq_destroy(gpsacq_t *h)
 {
+    DeviceGuard guard;
     if (!h) return;
     cudaSetDevice(h->device);
     cudaStreamSynchronize(h->stream);
@@ -793,6 +805,7 @@ static int search_device_impl(gpsacq *h, const uint8_t *d_bits, size_t n_blocks,
 
 int gpsacq_search_blocks_device(gpsacq_t *h, const uint8_t *d_bits, size_t n_blocks, const int32_t *d_sv, gpsacq_peak *d_out)
 {
+    DeviceGuard guard;
     if (!h || !d_bits || !d_out) return GPSACQ_EINVAL;
     if (h->mode != GPSACQ_MODE_REF) { h->err = "gpsacq_search_blocks needs a GPSACQ_MODE_REF handle"; return GPSACQ_EINVAL; }
     if (n_blocks == 0) return GPSACQ_OK;
@@ -810,6 +823,7 @@ int gpsacq_search_blocks_device(gpsacq_t *h, const uint8_t *d_bits, size_t n_blo
 // transfer is exposed.  Results come back with one device->host copy per batch.
 int gpsacq_search_blocks(gpsacq_t *h, const uint8_t *bits, size_t n_blocks, const int32_t *sv_of_block, gpsacq_peak *out)
 {
+    DeviceGuard guard;
     if (!h || (!bits && n_blocks) || (!out && n_blocks)) return GPSACQ_EINVAL;
     if (h->mode != GPSACQ_MODE_REF) { h->err = "gpsacq_search_blocks needs a GPSACQ_MODE_REF handle"; return GPSACQ_EINVAL; }
     CUDA_TRY(h, cudaSetDevice(h->device));
@@ -833,7 +847,11 @@ int gpsacq_search_blocks(gpsacq_t *h, const uint8_t *bits, size_t n_blocks, cons
             CUDA_TRY(h, cudaEventRecord(h->ev_copy[i], h->copy_stream));
             CUDA_TRY(h, cudaStreamWaitEvent(h->stream, h->ev_copy[i], 0));
             const int rc = search_device_impl(h, h->d_bits + lo * cb, n, h->d_sv + lo, (gpsacq_peak *)(h->d_peaks + lo), lo, i + 1 == n_slices);
-            if (rc) return rc;
+            if (rc) {           // nothing may still read the pinned staging buffers when the caller sees the error
+                cudaStreamSynchronize(h->copy_stream);
+                cudaStreamSynchronize(h->stream);
+                return rc;
+            }
         }
         h->have_batch = true;
         h->last_blocks = nb;
@@ -847,6 +865,7 @@ int gpsacq_search_blocks(gpsacq_t *h, const uint8_t *bits, size_t n_blocks, cons
 
 int gpsacq_acquire_device(gpsacq_t *h, const uint8_t *d_bits, size_t n_acq, gpsacq_peak *d_out)
 {
+    DeviceGuard guard;
     if (!h || !d_bits || !d_out) return GPSACQ_EINVAL;
     if (h->mode != GPSACQ_MODE_GRID) { h->err = "gpsacq_acquire needs a GPSACQ_MODE_GRID handle"; return GPSACQ_EINVAL; }
     if (n_acq == 0) return GPSACQ_OK;
@@ -856,6 +875,7 @@ int gpsacq_acquire_device(gpsacq_t *h, const uint8_t *d_bits, size_t n_acq, gpsa
 
 int gpsacq_acquire(gpsacq_t *h, const uint8_t *bits, size_t n_acq, gpsacq_peak *out)
 {
+    DeviceGuard guard;
     if (!h || (!bits && n_acq) || (!out && n_acq)) return GPSACQ_EINVAL;
     if (h->mode != GPSACQ_MODE_GRID) { h->err = "gpsacq_acquire needs a GPSACQ_MODE_GRID handle"; return GPSACQ_EINVAL; }
     CUDA_TRY(h, cudaSetDevice(h->device));
@@ -875,6 +895,7 @@ int gpsacq_acquire(gpsacq_t *h, const uint8_t *bits, size_t n_acq, gpsacq_peak *
 
 int gpsacq_iq8_to_bits(gpsacq_t *h, const void *iq, size_t n_samples, int format, double shift_hz, double fs, uint8_t *bits_out)
 {
+    DeviceGuard guard;
     if (!h || (!iq && n_samples) || (!bits_out && n_samples) || (format != GPSACQ_IQ_U8 && format != GPSACQ_IQ_S8) || !(fs > 0))
         return GPSACQ_EINVAL;
     if (n_samples == 0) return GPSACQ_OK;
@@ -918,7 +939,9 @@ int gpsacq_iq8_to_bits(gpsacq_t *h, const void *iq, size_t n_samples, int format
 int gpsacq_synth_capture(int device, double fs, double fc, const gpsacq_sat *sats, int n_sats, double noise_sigma,
                          double nav_bps, uint64_t seed, size_t n_samples, uint8_t *bits_out, void *d_bits_out)
 {
-    if (!(fs > 0) || n_sats < 0 || n_sats > SYNTH_MAX_SATS || (n_sats && !sats) || (!bits_out && !d_bits_out)) {
+    DeviceGuard guard;
+    if (!(fs > 0) || !std::isfinite(fs) || !std::isfinite(fc) || !std::isfinite(noise_sigma) || !std::isfinite(nav_bps) ||
+        n_sats < 0 || n_sats > SYNTH_MAX_SATS || (n_sats && !sats) || (!bits_out && !d_bits_out)) {
         g_create_error = "gpsacq_synth_capture: bad arguments (at most 16 satellites)"; return GPSACQ_EINVAL;
     }
     SynthParams p;
@@ -926,6 +949,10 @@ int gpsacq_synth_capture(int device, double fs, double fc, const gpsacq_sat *sat
     p.n_sats = n_sats; p.fs = fs; p.fc = fc; p.sigma = noise_sigma; p.nav_bps = nav_bps > 0 ? nav_bps : 50.0; p.seed = seed;
     for (int i = 0; i < n_sats; i++) {
         if (sats[i].prn < 1 || sats[i].prn > 32) { g_create_error = "gpsacq_synth_capture: prn out of range 1..32"; return GPSACQ_EINVAL; }
+        if (!std::isfinite(sats[i].amp) || !std::isfinite(sats[i].doppler_hz) || !std::isfinite(sats[i].carrier_phase_cycles) ||
+            !(sats[i].code_phase_chips >= 0.0 && sats[i].code_phase_chips < 1023.0) || !(fabs(sats[i].doppler_hz) < 1e7)) {
+            g_create_error = "gpsacq_synth_capture: amp / doppler_hz / carrier phase must be finite and code_phase_chips in [0, 1023)"; return GPSACQ_EINVAL;
+        }
         p.sat[i].prn = sats[i].prn; p.sat[i].t0 = kTaps[sats[i].prn - 1][0]; p.sat[i].t1 = kTaps[sats[i].prn - 1][1];
         p.sat[i].amp = sats[i].amp; p.sat[i].doppler_hz = sats[i].doppler_hz;
         p.sat[i].code_phase_chips = sats[i].code_phase_chips; p.sat[i].carrier_phase_cycles = sats[i].carrier_phase_cycles;
@@ -959,6 +986,7 @@ int gpsacq_stage_times(gpsacq_t *h, float ms[4])
 
 int gpsacq_get_replica_time(gpsacq_t *h, int sv, float *out)
 {
+    DeviceGuard guard;
     if (!h || !out || sv < 0 || sv >= 32) return GPSACQ_EINVAL;
     if (h->mode != GPSACQ_MODE_REF) { h->err = "probe needs a GPSACQ_MODE_REF handle"; return GPSACQ_EINVAL; }
     CUDA_TRY(h, cudaSetDevice(h->device));
@@ -979,6 +1007,7 @@ static int read_natural(gpsacq *h, const cf *src, int mode, float *out)
 
 int gpsacq_get_replica_spectrum(gpsacq_t *h, int sv, float *out)
 {
+    DeviceGuard guard;
     if (!h || !out || sv < 0 || sv >= 32) return GPSACQ_EINVAL;
     if (h->mode != GPSACQ_MODE_REF) { h->err = "probe needs a GPSACQ_MODE_REF handle"; return GPSACQ_EINVAL; }
     return read_natural(h, h->d_cext + (size_t)sv * 2 * h->n, 1, out);
@@ -986,6 +1015,7 @@ int gpsacq_get_replica_spectrum(gpsacq_t *h, int sv, float *out)
 
 int gpsacq_get_block_spectrum(gpsacq_t *h, size_t blk, float *out)
 {
+    DeviceGuard guard;
     if (!h || !out) return GPSACQ_EINVAL;
     if (h->mode != GPSACQ_MODE_REF) { h->err = "probe needs a GPSACQ_MODE_REF handle"; return GPSACQ_EINVAL; }
     if (!h->have_batch || blk >= h->last_blocks) { h->err = "block index outside the last batch"; return GPSACQ_ESTATE; }
@@ -994,6 +1024,7 @@ int gpsacq_get_block_spectrum(gpsacq_t *h, size_t blk, float *out)
 
 int gpsacq_get_cell_stats(gpsacq_t *h, size_t blk, gpsacq_cell *out)
 {
+    DeviceGuard guard;
     if (!h || !out) return GPSACQ_EINVAL;
     if (!h->have_batch || blk >= h->last_blocks) { h->err = "block index outside the last batch"; return GPSACQ_ESTATE; }
     CUDA_TRY(h, cudaSetDevice(h->device));
@@ -1049,6 +1080,34 @@ struct gpsacq_group {
     std::string err;
 };
 
+// ONE collective per batch: every device ends up with every device's (padded) records; device 0's copy goes to the
+// host.  Every NCCL / CUDA return code is checked; the first failure is reported (the group is still closed).
+static int group_allgather(gpsacq_group *g)
+{
+    const size_t ng = g->eng.size();
+    ncclResult_t first = 0;
+    const char *what = nullptr;
+    ncclResult_t r = g->nccl.GroupStart();
+    if (r != 0) { first = r; what = "ncclGroupStart"; }
+    for (size_t d = 0; d < ng && first == 0; d++) {
+        if (cudaSetDevice(g->dev[d]) != cudaSuccess) { g->err = "cudaSetDevice failed before ncclAllGather"; first = -1; what = "cudaSetDevice"; break; }
+        r = g->nccl.AllGather(g->eng[d]->d_peaks, g->d_all[d], (size_t)g->cap * sizeof(Peak), 0 /*ncclInt8*/, g->comm[d], g->eng[d]->stream);
+        if (r != 0) { first = r; what = "ncclAllGather"; }
+    }
+    r = g->nccl.GroupEnd();
+    if (r != 0 && first == 0) { first = r; what = "ncclGroupEnd"; }
+    if (first != 0) {
+        if (first > 0) g->err = std::string(what) + ": " + (g->nccl.GetErrorString ? g->nccl.GetErrorString(first) : "error");
+        return GPSACQ_ECUDA;
+    }
+    if (cudaSetDevice(g->dev[0]) != cudaSuccess) { g->err = "cudaSetDevice failed"; return GPSACQ_ECUDA; }
+    if (cudaMemcpyAsync(g->h_all.data(), g->d_all[0], ng * (size_t)g->cap * sizeof(Peak), cudaMemcpyDeviceToHost, g->eng[0]->stream) != cudaSuccess) { g->err = "D2H failed"; return GPSACQ_ECUDA; }
+    for (size_t d = 0; d < ng; d++) {
+        if (cudaSetDevice(g->dev[d]) != cudaSuccess || cudaStreamSynchronize(g->eng[d]->stream) != cudaSuccess) { g->err = "stream sync failed after ncclAllGather"; return GPSACQ_ECUDA; }
+    }
+    return GPSACQ_OK;
+}
+
 extern "C" {
 
 const char *gpsacq_group_last_error(const gpsacq_group_t *g) { return g ? g->err.c_str() : g_create_error.c_str(); }
@@ -1057,9 +1116,10 @@ gpsacq_t *gpsacq_group_engine(gpsacq_group_t *g, int i) { return (g && i >= 0 &&
 
 void gpsacq_group_destroy(gpsacq_group_t *g)
 {
+    DeviceGuard guard;
     if (!g) return;
     for (size_t i = 0; i < g->eng.size(); i++) {
-        cudaSetDevice(g->dev[i]);
+        if (cudaSetDevice(g->dev[i]) != cudaSuccess) fprintf(stderr, "libgpsacq: cudaSetDevice(%d) failed while destroying a group\n", g->dev[i]);
         if (i < g->d_all.size()) cudaFree(g->d_all[i]);
         if (g->use_nccl && i < g->comm.size() && g->comm[i]) g->nccl.CommDestroy(g->comm[i]);
         gpsacq_destroy(g->eng[i]);
@@ -1069,6 +1129,7 @@ void gpsacq_group_destroy(gpsacq_group_t *g)
 
 int gpsacq_group_create(const gpsacq_cfg *cfg, int n_gpus, const int32_t *devices, int use_nccl, gpsacq_group_t **out)
 {
+    DeviceGuard guard;
     if (!cfg || !out || n_gpus < 1 || (cfg->mode != GPSACQ_MODE_REF && cfg->mode != GPSACQ_MODE_GRID)) { g_create_error = "gpsacq_group_create: bad arguments"; return GPSACQ_EINVAL; }
     int ndop_full = 0;
     if (cfg->mode == GPSACQ_MODE_GRID) {
@@ -1102,15 +1163,26 @@ int gpsacq_group_create(const gpsacq_cfg *cfg, int n_gpus, const int32_t *device
     g->sv.resize(n_gpus);
     g->d_all.assign(n_gpus, nullptr);
     for (int i = 0; i < n_gpus; i++) {
-        cudaSetDevice(g->dev[i]);
+        if (cudaSetDevice(g->dev[i]) != cudaSuccess) { g_create_error = "group: cudaSetDevice failed"; gpsacq_group_destroy(g); return GPSACQ_ECUDA; }
         if (cudaMalloc(&g->d_all[i], (size_t)n_gpus * g->cap * sizeof(Peak)) != cudaSuccess) { g_create_error = "group: cudaMalloc failed"; gpsacq_group_destroy(g); return GPSACQ_ENOMEM; }
     }
     g->h_all.resize((size_t)n_gpus * g->cap);
-    if (use_nccl && n_gpus > 1 && nccl_load(g->nccl)) {
-        g->comm.assign(n_gpus, nullptr);
-        const ncclResult_t r = g->nccl.CommInitAll(g->comm.data(), n_gpus, g->dev.data());
-        if (r == 0) g->use_nccl = true;
-        else g->comm.clear();
+    if (use_nccl && n_gpus > 1) {
+        // NCCL was asked for: a fallback to the host gather is never silent (stderr + gpsacq_group_gather_kind()),
+        // and GPSACQ_REQUIRE_NCCL=1 turns it into an error
+        std::string why;
+        if (!nccl_load(g->nccl)) why = "libnccl.so.2 could not be loaded";
+        else {
+            g->comm.assign(n_gpus, nullptr);
+            const ncclResult_t r = g->nccl.CommInitAll(g->comm.data(), n_gpus, g->dev.data());
+            if (r == 0) g->use_nccl = true;
+            else { why = std::string("ncclCommInitAll: ") + (g->nccl.GetErrorString ? g->nccl.GetErrorString(r) : "error"); g->comm.clear(); }
+        }
+        if (!g->use_nccl) {
+            const char *req = getenv("GPSACQ_REQUIRE_NCCL");
+            if (req && *req && *req != '0') { g_create_error = "group: NCCL required but unavailable: " + why; gpsacq_group_destroy(g); return GPSACQ_ECUDA; }
+            fprintf(stderr, "libgpsacq: NCCL peak gather unavailable (%s); gathering the peak records through host memory\n", why.c_str());
+        }
     }
     *out = g;
     return GPSACQ_OK;
@@ -1118,6 +1190,7 @@ int gpsacq_group_create(const gpsacq_cfg *cfg, int n_gpus, const int32_t *device
 
 int gpsacq_group_search_blocks(gpsacq_group_t *g, const uint8_t *bits, size_t n_blocks, gpsacq_peak *out)
 {
+    DeviceGuard guard;
     if (!g || (!bits && n_blocks) || (!out && n_blocks)) return GPSACQ_EINVAL;
     const size_t ng = g->eng.size(), per_batch = (size_t)g->cap * ng;
     for (size_t done = 0; done < n_blocks;) {
@@ -1138,30 +1211,20 @@ int gpsacq_group_search_blocks(gpsacq_group_t *g, const uint8_t *bits, size_t n_
             if (rc) { g->err = h->err; return rc; }
         }
         if (g->use_nccl) {
-            // ONE collective per batch: every device ends up with every device's (padded) records
-            g->nccl.GroupStart();
-            for (size_t d = 0; d < ng; d++) {
-                cudaSetDevice(g->dev[d]);
-                g->nccl.AllGather(g->eng[d]->d_peaks, g->d_all[d], (size_t)g->cap * sizeof(Peak), 0 /*ncclInt8*/, g->comm[d], g->eng[d]->stream);
-            }
-            const ncclResult_t r = g->nccl.GroupEnd();
-            if (r != 0) { g->err = std::string("ncclAllGather: ") + (g->nccl.GetErrorString ? g->nccl.GetErrorString(r) : "error"); return GPSACQ_ECUDA; }
-            cudaSetDevice(g->dev[0]);
-            if (cudaMemcpyAsync(g->h_all.data(), g->d_all[0], ng * (size_t)g->cap * sizeof(Peak), cudaMemcpyDeviceToHost, g->eng[0]->stream) != cudaSuccess) { g->err = "D2H failed"; return GPSACQ_ECUDA; }
-            for (size_t d = 0; d < ng; d++) { cudaSetDevice(g->dev[d]); if (cudaStreamSynchronize(g->eng[d]->stream) != cudaSuccess) { g->err = "stream sync failed"; return GPSACQ_ECUDA; } }
+            const int rc = group_allgather(g);
+            if (rc) return rc;
             for (size_t d = 0; d < ng; d++)
                 memcpy(out + done + lo[d], g->h_all.data() + d * (size_t)g->cap, (lo[d + 1] - lo[d]) * sizeof(Peak));
         } else {
             for (size_t d = 0; d < ng; d++) {
                 gpsacq *h = g->eng[d];
                 const size_t n = lo[d + 1] - lo[d];
-                cudaSetDevice(h->device);
+                if (cudaSetDevice(h->device) != cudaSuccess) { g->err = "cudaSetDevice failed"; return GPSACQ_ECUDA; }
                 if (n && cudaMemcpyAsync(h->h_peaks, h->d_peaks, n * sizeof(Peak), cudaMemcpyDeviceToHost, h->stream) != cudaSuccess) { g->err = "D2H failed"; return GPSACQ_ECUDA; }
             }
             for (size_t d = 0; d < ng; d++) {
                 gpsacq *h = g->eng[d];
-                cudaSetDevice(h->device);
-                if (cudaStreamSynchronize(h->stream) != cudaSuccess) { g->err = "stream sync failed"; return GPSACQ_ECUDA; }
+                if (cudaSetDevice(h->device) != cudaSuccess || cudaStreamSynchronize(h->stream) != cudaSuccess) { g->err = "stream sync failed"; return GPSACQ_ECUDA; }
                 memcpy(out + done + lo[d], h->h_peaks, (lo[d + 1] - lo[d]) * sizeof(Peak));
             }
         }
@@ -1172,6 +1235,7 @@ int gpsacq_group_search_blocks(gpsacq_group_t *g, const uint8_t *bits, size_t n_
 
 int gpsacq_group_acquire(gpsacq_group_t *g, const uint8_t *bits, size_t n_acq, gpsacq_peak *out)
 {
+    DeviceGuard guard;
     if (!g || (!bits && n_acq) || (!out && n_acq)) return GPSACQ_EINVAL;
     if (g->eng[0]->mode != GPSACQ_MODE_GRID) { g->err = "gpsacq_group_acquire needs a GPSACQ_MODE_GRID group"; return GPSACQ_EINVAL; }
     const size_t ng = g->eng.size(), cap_acq = (size_t)g->cap / 32, acq_bytes = (size_t)g->eng[0]->chunk_bytes;
@@ -1187,26 +1251,17 @@ int gpsacq_group_acquire(gpsacq_group_t *g, const uint8_t *bits, size_t n_acq, g
             if (rc) { g->err = h->err; return rc; }
         }
         if (g->use_nccl) {
-            g->nccl.GroupStart();
-            for (size_t d = 0; d < ng; d++) {
-                cudaSetDevice(g->dev[d]);
-                g->nccl.AllGather(g->eng[d]->d_peaks, g->d_all[d], (size_t)g->cap * sizeof(Peak), 0 /*ncclInt8*/, g->comm[d], g->eng[d]->stream);
-            }
-            const ncclResult_t r = g->nccl.GroupEnd();
-            if (r != 0) { g->err = std::string("ncclAllGather: ") + (g->nccl.GetErrorString ? g->nccl.GetErrorString(r) : "error"); return GPSACQ_ECUDA; }
-            cudaSetDevice(g->dev[0]);
-            if (cudaMemcpyAsync(g->h_all.data(), g->d_all[0], ng * (size_t)g->cap * sizeof(Peak), cudaMemcpyDeviceToHost, g->eng[0]->stream) != cudaSuccess) { g->err = "D2H failed"; return GPSACQ_ECUDA; }
-            for (size_t d = 0; d < ng; d++) { cudaSetDevice(g->dev[d]); if (cudaStreamSynchronize(g->eng[d]->stream) != cudaSuccess) { g->err = "stream sync failed"; return GPSACQ_ECUDA; } }
+            const int rc = group_allgather(g);
+            if (rc) return rc;
         } else {
             for (size_t d = 0; d < ng; d++) {
                 gpsacq *h = g->eng[d];
-                cudaSetDevice(h->device);
+                if (cudaSetDevice(h->device) != cudaSuccess) { g->err = "cudaSetDevice failed"; return GPSACQ_ECUDA; }
                 if (cudaMemcpyAsync(h->h_peaks, h->d_peaks, nrec * sizeof(Peak), cudaMemcpyDeviceToHost, h->stream) != cudaSuccess) { g->err = "D2H failed"; return GPSACQ_ECUDA; }
             }
             for (size_t d = 0; d < ng; d++) {
                 gpsacq *h = g->eng[d];
-                cudaSetDevice(h->device);
-                if (cudaStreamSynchronize(h->stream) != cudaSuccess) { g->err = "stream sync failed"; return GPSACQ_ECUDA; }
+                if (cudaSetDevice(h->device) != cudaSuccess || cudaStreamSynchronize(h->stream) != cudaSuccess) { g->err = "stream sync failed"; return GPSACQ_ECUDA; }
                 memcpy(g->h_all.data() + d * (size_t)g->cap, h->h_peaks, nrec * sizeof(Peak));
             }
         }

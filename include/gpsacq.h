@@ -40,6 +40,9 @@
  * Threading: one host thread per handle at a time (the reference is not
  * re-entrant at all).  Several handles (e.g. one per GPU) may be used
  * concurrently from different threads.
+ *
+ * Current CUDA device: every entry point that has to select a device (create, search, acquire,
+ * probes, the group calls) restores the calling thread's current device before it returns.
  */
 #ifndef GPSACQ_H
 #define GPSACQ_H
@@ -51,7 +54,7 @@
 extern "C" {
 #endif
 
-#define GPSACQ_ABI_VERSION 3
+#define GPSACQ_ABI_VERSION 4
 
 #define GPSACQ_OK        0
 #define GPSACQ_EINVAL   (-1)   /* bad argument / unsupported configuration        */
@@ -79,6 +82,12 @@ typedef struct gpsacq_cfg {
     int32_t dop_count;   /*   n_doppler-bin grid (index 0 = bin -dmax).  dop_count = 0: the whole grid.    */
     int32_t reserved;    /*   This is how the (PRN x Doppler) grid of ONE acquisition is sharded over GPUs: */
                          /*   records keep absolute bin numbers, so shards merge by max snr / lower bin.    */
+    double  fs_replica;  /* REF only, 0 = fs: sampling rate the C/A replicas are generated for.  The reference reads
+                            FS once in SearchInit() for the code NCO (c/search_offline.cpp:76) but FC, FS and max_fo
+                            again on every Sample()/Correlate() (:127,:176,:190); a caller that changes the globals
+                            between SearchInit() and SearchTask() gets replicas at the old FS searched on the new grid.
+                            The C++ host passes the SearchInit()-time FS here when it rebuilds the engine for changed
+                            globals.                                                                              */
 } gpsacq_cfg;
 
 #define GPSACQ_MODE_REF  0   /* N = 40000 coherent window, bins of FS/N, one chunk per PRN
@@ -98,7 +107,8 @@ typedef struct gpsacq_peak {
     int32_t lo_shift;    /* winning Doppler bin, -dmax..+dmax  (*max_snr_dop, :198)            */
     int32_t ca_shift;    /* code phase in samples, 0..W-1      (*max_snr_i,   :198)            */
     int32_t sv;          /* 0-based satellite index (PRN-1) this chunk was searched for        */
-    int32_t flags;       /* bit0: snr >= 25 (the SearchTask() detection rule, :248)            */
+    int32_t flags;       /* bit0: snr >= 25 (the SearchTask() detection rule, :248);
+                            bit31: the device-side PRN map entry was outside 0..31 (searched as sv & 31) */
     int32_t reserved;
 } gpsacq_peak;
 

@@ -42,7 +42,7 @@ def test_struct_layouts_match_header(ga, tmp_path):
     subprocess.run(["gcc", f"-I{ROOT / 'include'}", str(src), "-o", str(exe)], check=True)
     got = [int(v) for v in subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.split()]
     want = [ctypes.sizeof(acq._Cfg), ctypes.sizeof(acq._Info), ga.PEAK_DTYPE.itemsize, ga.CELL_DTYPE.itemsize,
-            ga.HANDOFF_DTYPE.itemsize, ga.EVENT_DTYPE.itemsize, ga.EVENT_DTYPE.fields["start"][1], ctypes.sizeof(acq._Sat), 3]
+            ga.HANDOFF_DTYPE.itemsize, ga.EVENT_DTYPE.itemsize, ga.EVENT_DTYPE.fields["start"][1], ctypes.sizeof(acq._Sat), 4]
     assert got == want, (got, want)
     assert ctypes.sizeof(acq._Handoff) == ga.HANDOFF_DTYPE.itemsize
 
