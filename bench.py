@@ -12,7 +12,8 @@ with gps_test is defined and the only one the reference arm c
 
 A "step" is one batch of 224 runs = 7168 chunks x 73 bins = 523,264 correlations per GPU (~60 ms, so
 that 20 timed steps run for more than a second): forward FFT kernel, cell kernel (shifted conj-multiply
-+ pruned backward FFT + |.|^2 + peak), best-over-Doppler kernel, and for N > 1 one NCCL all-gather of
++ pruned backward FFT + |.|^2 + peak), best-over-Doppler kernel -- launched per 128 chunks so that the block
+spectra stay in L2 between the forward and the cell launch -- and for N > 1 one NCCL all-gather of
 the 7168 32-byte peak records per rank -- inside the timed region of BOTH value and e2e.
 Ranks work on different runs of the stream (weak scaling, no data-path collective).
 
@@ -135,7 +136,7 @@ class ClockSampler(threading.Thread):
         if not self.rows:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
         reasons = sorted(n for n, bit in self.BAD.items() if any(r[2] & bit for r in self.rows))
-        return {"sm_mhz": statistics.median(r[0] for r in self.rows), "sm_max_mhz": self.max_mhz,
+        return {"sm_mhz": statistics.median(r[0] for r in self.rows), "sm_mhz_min": min(r[0] for r in self.rows), "sm_max_mhz": self.max_mhz,
                 "power_w_max": max(r[1] for r in self.rows), "samples": len(self.rows), "reasons": reasons}
 
 
@@ -353,7 +354,11 @@ def run_engine(args, rank, world, local_rank):
             peak_gbs, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
         bpc = acq.info["bytes_per_corr"]
         cell_avg_ms = statistics.mean(cell_ms)
-        achieved = corr_per_step * bpc / (cell_avg_ms * 1e-3) / 1e9
+        # a step is cut into launches of blocks_per_launch chunks (their block spectra stay in L2); the stage events
+        # bracket the last launch triple of a step
+        launches_per_step = -(-nb // acq.info["blocks_per_launch"])
+        corr_per_launch = acq.info["blocks_per_launch"] * ndop
+        achieved = corr_per_launch * bpc / (cell_avg_ms * 1e-3) / 1e9
         # ncu-derived per-correlation figures of the same kernel (profiles/cell_kernel_ncu.json, made by tools/ncu_summary.py
         # + tools/ncu_flops.py from the committed capture): DRAM bytes, executed FP32 flops, issue-slot / FMA-pipe utilisation
         traffic = fp32 = None
@@ -361,8 +366,8 @@ def run_engine(args, rank, world, local_rank):
         prof = ROOT / "profiles" / "cell_kernel_ncu.json"
         if prof.exists():
             ncu = json.loads(prof.read_text())
-            traffic = ncu["dram_bytes_per_corr"] * corr_per_step
-            fp32 = ncu["fp32_flops_per_corr"] * corr_per_step / (cell_avg_ms * 1e-3) / 1e12
+            traffic = ncu["dram_bytes_per_corr"] * corr_per_launch
+            fp32 = ncu["fp32_flops_per_corr"] * corr_per_launch / (cell_avg_ms * 1e-3) / 1e12
         value = world * corr_per_step * args.steps / (total_ms * 1e-3)
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True,
@@ -370,7 +375,8 @@ def run_engine(args, rank, world, local_rank):
                 "config": workload_config(world),
                 "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak_gbs, "unit": "GB/s",
                              "frac": achieved / peak_gbs, "traffic": traffic, "kernel": "cell_kernel",
-                             "launch_ms": cell_avg_ms, "bytes_per_launch": corr_per_step * bpc, "peak_source": peak_src,
+                             "launch_ms": cell_avg_ms, "bytes_per_launch": corr_per_launch * bpc,
+                             "correlations_per_launch": corr_per_launch, "launches_per_step": launches_per_step, "peak_source": peak_src,
                              "whole_step_frac": value / world * bpc / 1e9 / peak_gbs,
                              "fp32_tflops": fp32, "fp32_peak_tflops": FP32_PEAK_TFLOPS,
                              "fp32_frac": None if fp32 is None else fp32 / FP32_PEAK_TFLOPS,
@@ -379,7 +385,7 @@ def run_engine(args, rank, world, local_rank):
                 "e2e": {"value": world * corr_per_step * args.steps / (e2e_ms * 1e-3), "unit": UNIT,
                         "h2d_bytes_per_step": nb * CHUNK + nb * 4, "d2h_bytes_per_step": nb * 32,
                         "ms_per_step": e2e_ms / args.steps},
-                "gpu_launches": ga_launches(args.steps),
+                "gpu_launches": 3 * launches_per_step * args.steps,      # fwd_kernel, cell_kernel, best_kernel per launch triple
                 "clocks": clocks,
                 "stage_ms": {k: round(v, 4) for k, v in stage.items()},
                 "detected_prns_last_step": detected}
@@ -425,7 +431,8 @@ def grid_c4_sharded(ga, dev, rank, world, dist):
     d_bits = torch.from_numpy(bits).to(dev)
     d_out = torch.zeros(32 * 32, dtype=torch.uint8, device=dev)
     d_all = torch.zeros(world * 32 * 32, dtype=torch.uint8, device=dev)
-    stream = torch.cuda.current_stream(dev)
+    stream = torch.cuda.Stream(device=dev)          # kernels, NCCL and the timing events all on this stream
+    torch.cuda.set_stream(stream)
     acq.set_stream(stream.cuda_stream)
 
     def one():
@@ -490,7 +497,8 @@ def grid_measure(ga, dev, peak_gbs, name):
     bits = ga.synth_capture_gpu(W * c["K"] * n_acq, c["fs"], c["fc"], sats, seed=3, device=dev.index)
     d_bits = torch.from_numpy(bits).to(dev)
     d_out = torch.zeros(n_acq * 32 * 32, dtype=torch.uint8, device=dev)
-    stream = torch.cuda.current_stream(dev)
+    stream = torch.cuda.Stream(device=dev)          # kernels and the timing events on this stream
+    torch.cuda.set_stream(stream)
     acq.set_stream(stream.cuda_stream)
     for _ in range(3):
         acq.acquire_device(d_bits.data_ptr(), n_acq, d_out.data_ptr())
@@ -513,10 +521,6 @@ def grid_measure(ga, dev, peak_gbs, name):
                     f"zero-padded embedding of the {W}-point correlation (DESIGN.md section 10)")}
     acq.close()
     return out
-
-
-def ga_launches(steps: int) -> int:
-    return 3 * steps            # GPSACQ_LAUNCHES_PER_BATCH: fwd_kernel, cell_kernel, best_kernel
 
 
 def main():

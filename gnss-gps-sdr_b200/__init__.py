@@ -9,8 +9,8 @@ The directory name contains a hyphen (it is the name the build contract asks for
 import it through ``load()`` in the repo-root ``gpsacq_loader.py`` or add the directory's
 parent to ``sys.path`` and use ``importlib``; inside the package everything is relative.
 """
-from .acq import (Acquisition, AcquisitionGroup, SearchService, handoff, HANDOFF_DTYPE, EVENT_DTYPE, synth_capture_gpu, GpsAcqError, PEAK_DTYPE, CELL_DTYPE, lib_path, load_library,
+from .acq import (Acquisition, AcquisitionGroup, SearchService, handoff, HANDOFF_DTYPE, EVENT_DTYPE, synth_capture_gpu, bits_to_iq8, bits_to_iq8_device, sig_gen_literal, GpsAcqError, PEAK_DTYPE, CELL_DTYPE, lib_path, load_library,
                   search_task_text, format_run, NUM_SATS, FFT_LEN, SNR_THRESHOLD)
 
-__all__ = ["Acquisition", "AcquisitionGroup", "SearchService", "handoff", "HANDOFF_DTYPE", "EVENT_DTYPE", "synth_capture_gpu", "GpsAcqError", "PEAK_DTYPE", "CELL_DTYPE", "lib_path", "load_library",
+__all__ = ["Acquisition", "AcquisitionGroup", "SearchService", "handoff", "HANDOFF_DTYPE", "EVENT_DTYPE", "synth_capture_gpu", "bits_to_iq8", "bits_to_iq8_device", "sig_gen_literal", "GpsAcqError", "PEAK_DTYPE", "CELL_DTYPE", "lib_path", "load_library",
            "search_task_text", "format_run", "NUM_SATS", "FFT_LEN", "SNR_THRESHOLD"]

@@ -37,7 +37,8 @@ class _Info(C.Structure):
                  "max_blocks", "device", "sm_count", "cell_ctas", "cell_threads", "cell_smem_bytes")] + \
                [("bytes_per_corr", C.c_int64), ("mode", C.c_int32), ("noncoh_blocks", C.c_int32),
                 ("block_bytes", C.c_int32), ("max_acq", C.c_int32), ("doppler_step", C.c_double),
-                ("dop_first", C.c_int32), ("n_doppler_full", C.c_int32)]
+                ("dop_first", C.c_int32), ("n_doppler_full", C.c_int32), ("blocks_per_launch", C.c_int32),
+                ("reserved", C.c_int32)]
 
 
 class _Sat(C.Structure):
@@ -88,6 +89,10 @@ def load_library() -> C.CDLL:
         "gpsacq_acquire": (C.c_int, [vp, vp, C.c_size_t, vp]),
         "gpsacq_acquire_device": (C.c_int, [vp, vp, C.c_size_t, vp]),
         "gpsacq_iq8_to_bits": (C.c_int, [vp, vp, C.c_size_t, C.c_int, C.c_double, C.c_double, vp]),
+        "gpsacq_iq8_to_bits_device": (C.c_int, [vp, vp, C.c_size_t, C.c_int, C.c_double, C.c_double, vp, vp]),
+        "gpsacq_bits_to_iq8": (C.c_int, [C.c_int, vp, C.c_size_t, C.c_size_t, C.c_double, C.c_double, C.c_int, vp]),
+        "gpsacq_bits_to_iq8_device": (C.c_int, [C.c_int, vp, C.c_size_t, C.c_size_t, C.c_double, C.c_double, C.c_int, vp, vp]),
+        "gpsacq_sig_gen_literal": (C.c_int, [C.c_int, C.c_int, vp, C.c_int, vp, vp]),
         "gpsacq_group_create": (C.c_int, [C.POINTER(_Cfg), C.c_int, i32p, C.c_int, C.POINTER(vp)]),
         "gpsacq_group_destroy": (None, [vp]),
         "gpsacq_group_search_blocks": (C.c_int, [vp, vp, C.c_size_t, vp]),
@@ -120,7 +125,8 @@ def load_library() -> C.CDLL:
 
 ABI_SYMBOLS = ("gpsacq_create", "gpsacq_destroy", "gpsacq_last_error", "gpsacq_get_info",
                "gpsacq_set_stream", "gpsacq_synchronize", "gpsacq_search_blocks",
-               "gpsacq_search_blocks_device", "gpsacq_acquire", "gpsacq_acquire_device", "gpsacq_iq8_to_bits", "gpsacq_group_create",
+               "gpsacq_search_blocks_device", "gpsacq_acquire", "gpsacq_acquire_device", "gpsacq_iq8_to_bits", "gpsacq_iq8_to_bits_device",
+               "gpsacq_bits_to_iq8", "gpsacq_bits_to_iq8_device", "gpsacq_sig_gen_literal", "gpsacq_group_create",
                "gpsacq_group_destroy", "gpsacq_group_search_blocks", "gpsacq_group_acquire", "gpsacq_group_gather_kind", "gpsacq_group_last_error",
                "gpsacq_group_engine", "gpsacq_handoff_compute", "gpsacq_service_create", "gpsacq_service_destroy",
                "gpsacq_service_feed", "gpsacq_service_enable", "gpsacq_service_signal_lost", "gpsacq_service_state",
@@ -232,6 +238,12 @@ class Acquisition:
                                                  fs if fs is not None else self.fs, out.ctypes.data))
         return out
 
+    def iq8_to_bits_device(self, d_iq_ptr: int, n_samples: int, shift_hz: float, fs: float, d_bits_ptr: int, d_sums_ptr: int,
+                           signed: bool = False):
+        """Device-buffer form of iq8_to_bits (asynchronous on the handle's stream apart from the read-back of the mean)."""
+        self._check(self._lib.gpsacq_iq8_to_bits_device(self._h, d_iq_ptr, n_samples, 1 if signed else 0, shift_hz, fs,
+                                                        d_bits_ptr, d_sums_ptr))
+
     def search_blocks_device(self, d_bits_ptr: int, n_blocks: int, d_sv_ptr: int | None, d_out_ptr: int):
         """Asynchronous device-pointer variant (raw CUDA device addresses)."""
         self._check(self._lib.gpsacq_search_blocks_device(self._h, d_bits_ptr, n_blocks, d_sv_ptr, d_out_ptr))
@@ -285,6 +297,37 @@ def synth_capture_gpu(n_samples: int, fs: float, fc: float, sats, seed: int = 1,
     if rc != 0:
         msg = lib.gpsacq_last_error(None)
         raise GpsAcqError(f"gpsacq_synth_capture failed ({rc}): {msg.decode() if msg else '?'}")
+    return out
+
+
+def _free_call(rc: int, what: str):
+    if rc != 0:
+        msg = load_library().gpsacq_last_error(None)
+        raise GpsAcqError(f"{what} failed ({rc}): {msg.decode() if msg else '?'}")
+
+
+def bits_to_iq8(bits, fc: float, fs: float, amplitude: int = 30, first_sample: int = 0, device: int = 0) -> np.ndarray:
+    """The reference's c/conv_1bit_bin_to_hackrf_bin.cpp on the GPU: packed 1-bit real-IF samples -> interleaved int8
+    I,Q at baseband (16 output bytes per input byte).  fc / fs: what the reference takes from c/gps.h (2.6e6 / 10e6)."""
+    buf = np.ascontiguousarray(np.frombuffer(bits, np.uint8) if not isinstance(bits, np.ndarray) else bits)
+    out = np.zeros(16 * buf.size, np.int8)
+    _free_call(load_library().gpsacq_bits_to_iq8(device, buf.ctypes.data, buf.size, first_sample, fc, fs, amplitude, out.ctypes.data),
+               "gpsacq_bits_to_iq8")
+    return out
+
+
+def bits_to_iq8_device(d_bits_ptr: int, n_bytes: int, fc: float, fs: float, d_out_ptr: int, amplitude: int = 30,
+                       first_sample: int = 0, device: int = -1, stream_ptr: int | None = None):
+    _free_call(load_library().gpsacq_bits_to_iq8_device(device, d_bits_ptr, n_bytes, first_sample, fc, fs, amplitude, d_out_ptr, stream_ptr),
+               "gpsacq_bits_to_iq8_device")
+
+
+def sig_gen_literal(prn: int, nav_bits01, device: int = 0) -> np.ndarray:
+    """gps_sig_gen.m:8-41 on the GPU, literally (x8 zero-stuff, 20 periods per NAV bit, rcosine(1,8), carrier at fs/4,
+    sign, 'ubit1'): the bytes of the file it writes for satellite `prn` and the given NAV bits."""
+    nav = np.ascontiguousarray(nav_bits01, np.uint8)
+    out = np.zeros((nav.size * 163680 + 48 + 7) // 8, np.uint8)
+    _free_call(load_library().gpsacq_sig_gen_literal(device, prn, nav.ctypes.data, nav.size, out.ctypes.data, None), "gpsacq_sig_gen_literal")
     return out
 
 

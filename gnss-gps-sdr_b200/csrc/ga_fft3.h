@@ -123,6 +123,24 @@ GA_HD void cell_sub_offsets(int s, int dop, int &sp, int &eoff)
     eoff = q % G::N2; if (eoff < 0) eoff += G::N2;
 }
 
+// Which pass-A butterfly runs on lane-slot jj (0 <= jj < NA) of the CTA.  The tile pitch of a b-row is RC+1 (odd, for
+// passes B and C), so 16 lanes that straddle two b-rows store to 16 slots with one slot skipped in the middle: the
+// first and the last of them share a bank pair and the 64-bit store takes two wavefronts instead of one (20 % of all
+// shared-memory wavefronts of the kernel).  For RB = RC = 20 the 400 butterflies are therefore dealt in half-warps that
+// never do that: 20 half-warps (b, c = 0..15) and 5 half-warps of the left-over columns c = 16..19 of four rows whose
+// bank offsets are 4 apart (rows g, g+4, g+8, g+12; the last group takes rows 16..19 and keeps a 3-slot overlap).
+// The operand loads stay whole 32-byte sectors (16 or 4 consecutive columns).
+template <class G> GA_HD int passA_slot_to_j(int jj)
+{
+    if (G::RB == 20 && G::RC == 20) {
+        const int h = jj >> 4, i = jj & 15;
+        if (h < 20) return 20 * h + i;
+        const int g = h - 20, r = i >> 2, row = g < 4 ? g + 4 * r : 16 + r;
+        return 20 * row + 16 + (i & 3);
+    }
+    return jj;
+}
+
 // pass A of a cell: thread j of NA.  xs = conj(X) sub-sequence s (N2 values),
 // cs = Cext[sv][sp] + eoff.
 template <class G, int ORI = 0>

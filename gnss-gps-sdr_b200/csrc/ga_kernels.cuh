@@ -27,6 +27,12 @@ constexpr int K1TAB_MAX = 128;     // N1*N1 <= 100
 constexpr int NGEOM = 12;      // 3 REF geometries (N = 40000) + 4 GRID embeddings (N1 = 2) + 5 exact-length GRID geometries (N1 = 1)
 __constant__ cf c_ktab[NGEOM][KTAB_MAX];
 __constant__ cf c_k1tab[NGEOM][K1TAB_MAX];
+// REF mode, search windows longer than N2 (sampling rates above 10 MHz): output segment m = lags [m*N2, (m+1)*N2)
+// of the N-point backward transform is the same sum of sub-sequence transforms with the extra factor
+// exp(2*pi*i*s*m/N1) on term s:  y[tau + N2*m] = sum_s w_N^(s*tau) * w_N1^(s*m) * IFFT_N2(P_s)[tau].
+// c_ktab_seg[m][s*RC + w] = ktab[s*RC + w] * exp(2*pi*i*s*m/N1)   (geometry 4 x 10000 only)
+constexpr int MAX_SEG = 4;
+__constant__ cf c_ktab_seg[MAX_SEG][KTAB_MAX];
 
 // ---------------------------------------------------------------------------------
 // C/A replica in the time domain.  One CTA per PRN.  chip_idx/blendA/blendB are the
@@ -228,10 +234,20 @@ constexpr int cell_minb(int threads) { return threads <= 128 ? 3 : 2; }
 // different sub-partitions: 10/10/10/9 tasks per pass round.  Rotating the warp -> task map per CTA on top of that
 // was measured at -10 %: it re-aligns the heavy warps onto one sub-partition.)
 
-template <class G, int T, int NW, int GID>
+// (Measured in round 2 and dropped, one B200, 128-chunk launches: pass-B twiddles from a per-sub-sequence table in shared
+// memory instead of the product tree: 8.40 -> 7.56 M corr/s (19 more LDS per butterfly cost more than the 38 packed
+// multiplies they save); operands of a warp's first pass-A task loaded before the barrier that ends the previous pass C
+// (167 registers): 8.40 -> 8.31 M corr/s.)
+#ifndef GA_PERM_A
+#define GA_PERM_A 1         // bank-conflict-free dealing of the pass-A butterflies (ga_fft3.h passA_slot_to_j)
+#endif
+// SEG: the work item is (chunk, Doppler bin, output segment) -- nseg segments of N2 lags each cover a window of up to
+// N samples; the per-segment records are merged by merge_seg_kernel.  SEG = false is the plain kernel (one segment).
+template <class G, int T, int NW, int GID, bool SEG = false>
 __global__ void __launch_bounds__(T, cell_minb(T)) cell_kernel_tm(const cf *__restrict__ xd, const cf *__restrict__ cext,
                                                        const int *__restrict__ sv_of_block, const cf *__restrict__ tw,
-                                                       int n_cells, int n_dop, int dmax, int wlen, CellStat *__restrict__ cells)
+                                                       int n_cells, int n_dop, int dmax, int wlen, CellStat *__restrict__ cells,
+                                                       int nseg = 1, int blk0 = 0)
 {
     static_assert(T % 32 == 0, "tcgen05.ld/st are warp-collective: whole warps only");
     constexpr int NWARP = T / 32;
@@ -268,21 +284,23 @@ __global__ void __launch_bounds__(T, cell_minb(T)) cell_kernel_tm(const cf *__re
     const int vw = wid;
 
     for (int cell = blockIdx.x; cell < n_cells; cell += gridDim.x) {
-        const int blk = cell / n_dop, dop = cell - blk * n_dop - dmax;
-        const int sv = (sv_of_block ? sv_of_block[blk] : blk) & 31;     // caller-supplied device maps are not trusted: see best_kernel
+        int item = cell, seg = 0;
+        if (SEG) { seg = cell % nseg; item = cell / nseg; }
+        const int blk = item / n_dop, dop = item - blk * n_dop - dmax;
+        const int wl = SEG ? wlen - seg * G::N2 : wlen;                 // lags of this segment inside the search window
+        const int sv = (sv_of_block ? sv_of_block[blk] : blk + blk0) & 31;     // caller-supplied device maps are not trusted: see best_kernel
         const cf *xb = xd + (size_t)blk * G::N;
         const cf *cb = cext + (size_t)sv * (2 * G::N);
         float best = 0.0f, sum = 0.0f;
         int besti = 0;
-
         for (int s = 0; s < G::N1; s++) {
             int sp, eoff;
             cell_sub_offsets<G>(s, dop, sp, eoff);
             const cf *xs = xb + (size_t)s * G::N2;
             const cf *cs = cb + (size_t)sp * (2 * G::N2) + eoff;
             for_tasks<ITA>([&](int it) {
-                const int j = (vw + it * NWARP) * 32 + lane;
-                if (j < G::NA) cell_passA<G>(j, s, xs, cs, tw, sm);
+                const int jj = (vw + it * NWARP) * 32 + lane;
+                if (jj < G::NA) cell_passA<G>(GA_PERM_A ? passA_slot_to_j<G>(jj) : jj, s, xs, cs, tw, sm);
             });
             __syncthreads();
             for_tasks<ITB>([&](int it) {
@@ -290,7 +308,7 @@ __global__ void __launch_bounds__(T, cell_minb(T)) cell_kernel_tm(const cf *__re
                 if (j < G::NB) passB<G, +1>(j, s, tw, sm);
             });
             __syncthreads();
-            const cf *ks = c_ktab[GID] + s * G::RC;
+            const cf *ks = (SEG ? c_ktab_seg[seg] : c_ktab[GID]) + s * G::RC;
             for_tasks<ITC>([&](int it) {
                 const int task = vw + it * NWARP;
                 if (task < NTC) {          // warp-uniform
@@ -323,7 +341,7 @@ __global__ void __launch_bounds__(T, cell_minb(T)) cell_kernel_tm(const cf *__re
 #pragma unroll
                         for (int w = 0; w < NW; w++) {
                             const int tau = tau0 + G::OUT_STRIDE * w;
-                            if (tau < wlen) {
+                            if (tau < wl) {
                                 const float pwr = fmaf(a[2 * w], a[2 * w], a[2 * w + 1] * a[2 * w + 1]);
                                 if (pwr > best || (pwr == best && tau < besti)) { best = pwr; besti = tau; }
                                 sum += pwr;
@@ -377,7 +395,7 @@ __global__ void __launch_bounds__(T, cell_minb(T)) cell_kernel_tm(const cf *__re
                 sum += os;
             }
             if (lane == 0) {
-                CellStat r; r.max_pwr = best; r.tot_pwr = sum; r.max_idx = besti; r.pad = 0;
+                CellStat r; r.max_pwr = best; r.tot_pwr = sum; r.max_idx = besti + (SEG ? seg * G::N2 : 0); r.pad = 0;
                 cells[cell] = r;
             }
         }
@@ -387,13 +405,29 @@ __global__ void __launch_bounds__(T, cell_minb(T)) cell_kernel_tm(const cf *__re
     if (wid == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tm_base), "r"(TM_COLS) : "memory");
 }
 
+// per-segment records [pair][nseg] -> one record per (chunk, Doppler bin): the reference's single scan over i < W
+// (c/search_offline.cpp:190-194) visits the segments in ascending order, so the first maximum is the lowest segment's on
+// equal power and the power sum adds the segment sums in that order.
+__global__ void merge_seg_kernel(const CellStat *__restrict__ seg_cells, int n_pairs, int nseg, CellStat *__restrict__ cells)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_pairs) return;
+    CellStat r = seg_cells[(size_t)i * nseg];
+    for (int m = 1; m < nseg; m++) {
+        const CellStat c = seg_cells[(size_t)i * nseg + m];
+        if (c.max_pwr > r.max_pwr) { r.max_pwr = c.max_pwr; r.max_idx = c.max_idx; }
+        r.tot_pwr += c.tot_pwr;
+    }
+    cells[i] = r;
+}
+
 // ---------------------------------------------------------------------------------
 // snr per Doppler bin and best over Doppler, one thread per block (chunk).
 // ave_pwr = tot_pwr/W ; snr = max_pwr/ave_pwr ; strictly-greater scan in ascending dop
 // from max_snr = 0 (c/search_offline.cpp:173,196-198); detection rule snr >= 25 (:248).
 // ---------------------------------------------------------------------------------
 __global__ void best_kernel(const CellStat *__restrict__ cells, const int *__restrict__ sv_of_block,
-                            int n_blocks, int n_dop, int dmax, int wlen, Peak *__restrict__ peaks)
+                            int n_blocks, int n_dop, int dmax, int wlen, Peak *__restrict__ peaks, int blk0 = 0)
 {
     // one warp per chunk: lanes take Doppler bins k, k+32, ... in ascending order, then a shuffle
     // reduction that prefers the higher snr and, on equal snr, the LOWER bin -- the same winner as the
@@ -420,7 +454,7 @@ __global__ void best_kernel(const CellStat *__restrict__ cells, const int *__res
         if (k != 0x7fffffff) {
             p.lo_shift = k - dmax; p.ca_shift = c[k].max_idx; p.max_pwr = c[k].max_pwr; p.tot_pwr = c[k].tot_pwr;
         }
-        p.sv = sv_of_block ? sv_of_block[blk] : (blk & 31);
+        p.sv = sv_of_block ? sv_of_block[blk] : ((blk + blk0) & 31);
         p.flags = (snr < 25.0f) ? 0 : 1;
         if (p.sv < 0 || p.sv > 31) p.flags |= (int)0x80000000u;    // device-side PRN map entry out of range: searched as sv & 31
         p.reserved = 0;

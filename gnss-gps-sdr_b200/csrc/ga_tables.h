@@ -30,6 +30,21 @@ template <class G> inline std::vector<cf> make_ktab()
     return t;
 }
 
+// ktab of output segment m (lags [m*N2, (m+1)*N2) of the N-point backward transform): the term of sub-sequence s
+// carries the extra factor exp(+2*pi*i*s*m/N1), computed here in long double and rounded once
+template <class G> inline std::vector<cf> make_ktab_seg(int m)
+{
+    std::vector<cf> t((size_t)G::N1 * G::RC);
+    const long double two_pi = 2.0L * 3.14159265358979323846264338327950288L;
+    for (int s = 0; s < G::N1; s++)
+        for (int w = 0; w < G::RC; w++) {
+            const long double a = two_pi * (long double)((s * w) % (G::N1 * G::RC)) / (long double)(G::N1 * G::RC) +
+                                  two_pi * (long double)((s * m) % G::N1) / (long double)G::N1;
+            t[(size_t)s * G::RC + w] = mk((float)cosl(a), (float)sinl(a));
+        }
+    return t;
+}
+
 // k1tab[s*N1 + n1] = exp(-2*pi*i*n1*s/N1): first (radix-N1) stage of the forward transform
 template <class G> inline std::vector<cf> make_k1tab()
 {

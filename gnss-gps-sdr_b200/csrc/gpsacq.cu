@@ -135,6 +135,10 @@ struct gpsacq {
     gpsacq_cfg cfg;
     int gid, n, n1, n2, w, dmax, ndop, chunk_bytes, chunk_samples, cap, device, sm_count;
     int cell_ctas, cell_threads, cell_smem, cell_nw;
+    double *d_iq_tab; unsigned long long iq_tab_p, iq_tab_q; bool iq_tab_neg;     // 8-bit front-end: phasor table of the last shift
+    int sub_blocks, last_launch_blocks; // REF: chunks per kernel launch (a batch is cut into launches whose block spectra stay in L2)
+    int nseg;                          // REF: output segments of N2 lags per cell (1 unless W > N2, i.e. FS > 10 MHz)
+    CellStat *d_cells_seg;
     int mode, kblocks, wipe_m, block_bytes, cap_acq;
     int q_min, n_q;                    // GRID, native path: replica spectra are stored rotated by -q for q_min <= q < q_min + n_q
     cf *d_crot;
@@ -178,26 +182,31 @@ struct gpsacq {
 // ---- kernel dispatch ------------------------------------------------------------------
 // (the measured-and-slower variants of the hot kernel -- register accumulators, software-pipelined operand prefetch,
 // rotating shared-memory layouts -- are kept outside the product under tools/experiments/)
-template <class G, int T, int NW, int GID> struct CellKernel {
-    static auto get() { return cell_kernel_tm<G, T, NW, GID>; }
+template <class G, int T, int NW, int GID, bool SEG = false> struct CellKernel {
+    static auto get() { return cell_kernel_tm<G, T, NW, GID, SEG>; }
 };
 
-template <class G, int T, int NW, int GID>
-static int launch_cells_t(gpsacq *h, size_t n_blocks, const int *d_sv, size_t off)
+template <class G, int T, int NW, int GID, bool SEG = false>
+static int launch_cells_t(gpsacq *h, size_t n_blocks, const int *d_sv, size_t off, int blk0)
 {
     // off: first workspace slot (block spectra / cell records) of this (sub-)batch
-    const int n_cells = (int)(n_blocks * (size_t)h->ndop);
+    const int n_pairs = (int)(n_blocks * (size_t)h->ndop), n_cells = n_pairs * (SEG ? h->nseg : 1);
     const int grid = std::min(n_cells, h->cell_ctas);
-    CellKernel<G, T, NW, GID>::get()<<<grid, T, h->cell_smem, h->stream>>>(
-        h->d_xd + off * (size_t)h->n, h->d_cext, d_sv, h->d_tw, n_cells, h->ndop, h->dmax, h->w, h->d_cells + off * (size_t)h->ndop);
+    CellStat *out = SEG ? h->d_cells_seg + off * (size_t)h->ndop * h->nseg : h->d_cells + off * (size_t)h->ndop;
+    CellKernel<G, T, NW, GID, SEG>::get()<<<grid, T, h->cell_smem, h->stream>>>(
+        h->d_xd + off * (size_t)h->n, h->d_cext, d_sv, h->d_tw, n_cells, h->ndop, h->dmax, h->w, out, h->nseg, blk0);
     CUDA_TRY(h, cudaGetLastError());
+    if (SEG) {
+        merge_seg_kernel<<<(n_pairs + 255) / 256, 256, 0, h->stream>>>(out, n_pairs, h->nseg, h->d_cells + off * (size_t)h->ndop);
+        CUDA_TRY(h, cudaGetLastError());
+    }
     return 0;
 }
 
-template <class G, int T, int NW, int GID>
+template <class G, int T, int NW, int GID, bool SEG = false>
 static int setup_cells_t(gpsacq *h)
 {
-    auto kern = CellKernel<G, T, NW, GID>::get();
+    auto kern = CellKernel<G, T, NW, GID, SEG>::get();
     h->cell_smem = (int)(G::SMEM_ELEMS * sizeof(cf));
     h->cell_threads = T;
     h->cell_nw = NW;
@@ -254,23 +263,25 @@ static int setup_cells(gpsacq *h)
         return h->w <= 14 * G8000::OUT_STRIDE ? setup_cells_t<G8000, CELL_T_8000, 14, GID_8000>(h)
                                               : setup_cells_t<G8000, CELL_T_8000_WIDE, 20, GID_8000>(h);
     default:
+        if (h->nseg > 1) return setup_cells_t<G10000, CELL_T_10000, 20, GID_10000, true>(h);
         return h->w <= 17 * G10000::OUT_STRIDE ? setup_cells_t<G10000, CELL_T_10000, 17, GID_10000>(h)
                                                : setup_cells_t<G10000, CELL_T_10000, 20, GID_10000>(h);
     }
 }
 
-static int launch_cells(gpsacq *h, size_t n_blocks, const int *d_sv, size_t off = 0)
+static int launch_cells(gpsacq *h, size_t n_blocks, const int *d_sv, size_t off, int blk0)
 {
     switch (h->gid) {
     case GID_4000:
-        return h->cell_nw == 7 ? launch_cells_t<G4000, CELL_T_4000, 7, GID_4000>(h, n_blocks, d_sv, off)
-                               : launch_cells_t<G4000, CELL_T_4000, 10, GID_4000>(h, n_blocks, d_sv, off);
+        return h->cell_nw == 7 ? launch_cells_t<G4000, CELL_T_4000, 7, GID_4000>(h, n_blocks, d_sv, off, blk0)
+                               : launch_cells_t<G4000, CELL_T_4000, 10, GID_4000>(h, n_blocks, d_sv, off, blk0);
     case GID_8000:
-        return h->cell_nw == 14 ? launch_cells_t<G8000, CELL_T_8000, 14, GID_8000>(h, n_blocks, d_sv, off)
-                                : launch_cells_t<G8000, CELL_T_8000_WIDE, 20, GID_8000>(h, n_blocks, d_sv, off);
+        return h->cell_nw == 14 ? launch_cells_t<G8000, CELL_T_8000, 14, GID_8000>(h, n_blocks, d_sv, off, blk0)
+                                : launch_cells_t<G8000, CELL_T_8000_WIDE, 20, GID_8000>(h, n_blocks, d_sv, off, blk0);
     default:
-        return h->cell_nw == 17 ? launch_cells_t<G10000, CELL_T_10000, 17, GID_10000>(h, n_blocks, d_sv, off)
-                                : launch_cells_t<G10000, CELL_T_10000, 20, GID_10000>(h, n_blocks, d_sv, off);
+        if (h->nseg > 1) return launch_cells_t<G10000, CELL_T_10000, 20, GID_10000, true>(h, n_blocks, d_sv, off, blk0);
+        return h->cell_nw == 17 ? launch_cells_t<G10000, CELL_T_10000, 17, GID_10000>(h, n_blocks, d_sv, off, blk0)
+                                : launch_cells_t<G10000, CELL_T_10000, 20, GID_10000>(h, n_blocks, d_sv, off, blk0);
     }
 }
 
@@ -339,7 +350,7 @@ static void free_all(gpsacq *h)
     if (!h) return;
     cudaFree(h->d_tw); cudaFree(h->d_lo); cudaFree(h->d_chip_idx); cudaFree(h->d_blend_a); cudaFree(h->d_blend_b);
     cudaFree(h->d_repl_time); cudaFree(h->d_cext); cudaFree(h->d_xd); cudaFree(h->d_nat); cudaFree(h->d_bits);
-    cudaFree(h->d_crot); cudaFree(h->d_sv); cudaFree(h->d_wipe); cudaFree(h->d_xg); cudaFree(h->d_code_w); cudaFree(h->d_cells); cudaFree(h->d_peaks);
+    cudaFree(h->d_crot); cudaFree(h->d_iq_tab); cudaFree(h->d_cells_seg); cudaFree(h->d_sv); cudaFree(h->d_wipe); cudaFree(h->d_xg); cudaFree(h->d_code_w); cudaFree(h->d_cells); cudaFree(h->d_peaks);
     cudaFreeHost(h->h_bits); cudaFreeHost(h->h_sv); cudaFreeHost(h->h_peaks);
     for (int i = 0; i < 4; i++) if (h->ev[i]) cudaEventDestroy(h->ev[i]);
     for (int i = 0; i < 8; i++) if (h->ev_copy[i]) cudaEventDestroy(h->ev_copy[i]);
@@ -388,10 +399,17 @@ static int create_impl(gpsacq *h)
     h->chunk_samples = ((h->n + 4095) / 4096) * 4096;         // whole 512-byte packets (:129,:135-141)
     h->chunk_bytes = h->chunk_samples / 8;
     h->cap = c.max_blocks > 0 ? c.max_blocks : 512;
+    {   // chunks per launch: 128 x 320 KB = 41 MB of block spectra + 20 MB of replica spectra stay L2-resident
+        const char *e = getenv("GPSACQ_SUB_BLOCKS");
+        h->sub_blocks = (e && atoi(e) > 0) ? atoi(e) : 128;
+    }
     if (h->w <= G4000::N2) { h->gid = GID_4000; h->n1 = G4000::N1; h->n2 = G4000::N2; }
     else if (h->w <= G8000::N2) { h->gid = GID_8000; h->n1 = G8000::N1; h->n2 = G8000::N2; }
-    else if (h->w <= G10000::N2) { h->gid = GID_10000; h->n1 = G10000::N1; h->n2 = G10000::N2; }
-    else { h->err = "sampling rates above 10 MHz (W > 10000) are not supported yet"; return GPSACQ_EINVAL; }
+    else { h->gid = GID_10000; h->n1 = G10000::N1; h->n2 = G10000::N2; }
+    // FS above 10 MHz (the reference takes any FS with FS/1000 <= FFT_LEN, :190): the window is covered by
+    // nseg = ceil(W / 10000) output segments of the 4 x 10000 geometry (ga_kernels.cuh, c_ktab_seg)
+    h->nseg = (h->w + h->n2 - 1) / h->n2;
+    if (h->nseg > MAX_SEG) { h->err = "search window longer than fft_len"; return GPSACQ_EINVAL; }
     if (h->dmax >= h->n2) { h->err = "max_fo too large for this fft_len"; return GPSACQ_EINVAL; }
 
     { const int rc_dev = open_device(h); if (rc_dev) return rc_dev; }
@@ -409,6 +427,7 @@ static int create_impl(gpsacq *h)
     CUDA_TRY(h, cudaMalloc(&h->d_bits, cap * (size_t)h->chunk_bytes));
     CUDA_TRY(h, cudaMalloc(&h->d_sv, cap * sizeof(int)));
     CUDA_TRY(h, cudaMalloc(&h->d_cells, cap * (size_t)h->ndop * sizeof(CellStat)));
+    if (h->nseg > 1) CUDA_TRY(h, cudaMalloc(&h->d_cells_seg, cap * (size_t)h->ndop * h->nseg * sizeof(CellStat)));
     CUDA_TRY(h, cudaMalloc(&h->d_peaks, cap * sizeof(Peak)));
     CUDA_TRY(h, cudaMallocHost(&h->h_bits, cap * (size_t)h->chunk_bytes));
     CUDA_TRY(h, cudaMallocHost(&h->h_sv, cap * sizeof(int)));
@@ -420,6 +439,10 @@ static int create_impl(gpsacq *h)
     int rc = h->gid == GID_4000 ? upload_const_t<G4000, GID_4000>(h)
            : h->gid == GID_8000 ? upload_const_t<G8000, GID_8000>(h) : upload_const_t<G10000, GID_10000>(h);
     if (rc) return rc;
+    for (int m = 0; h->nseg > 1 && m < h->nseg; m++) {
+        std::vector<cf> km = make_ktab_seg<G10000>(m);
+        CUDA_TRY(h, cudaMemcpyToSymbol(c_ktab_seg, km.data(), km.size() * sizeof(cf), (size_t)m * KTAB_MAX * sizeof(cf)));
+    }
     std::vector<unsigned char> lo;
     build_lo_table(c.fc, c.fs, h->chunk_samples, lo);
     CUDA_TRY(h, cudaMemcpy(h->d_lo, lo.data(), lo.size(), cudaMemcpyHostToDevice));
@@ -714,6 +737,9 @@ static int acquire_device_impl(gpsacq *h, const uint8_t *d_bits, size_t n_acq, g
     return GPSACQ_OK;
 }
 
+static int iq8_convert_piece(gpsacq *h, const unsigned char *d_iq, size_t n, size_t n0, int format, double mi, double mq,
+                             double shift_hz, double fs, unsigned char *d_bits);
+
 // ---- ABI -------------------------------------------------------------------------------
 extern "C" {
 
@@ -763,6 +789,7 @@ int gpsacq_get_info(const gpsacq_t *h, gpsacq_info *info)
     info->device = h->device; info->sm_count = h->sm_count;
     info->cell_ctas = h->cell_ctas; info->cell_threads = h->cell_threads; info->cell_smem_bytes = h->cell_smem;
     info->bytes_per_corr = 2LL * (h->mode == GPSACQ_MODE_GRID ? h->w : h->n) * 8 + 16;
+    info->blocks_per_launch = h->mode == GPSACQ_MODE_GRID ? 0 : (h->last_launch_blocks > 0 ? h->last_launch_blocks : h->sub_blocks);
     info->mode = h->mode; info->noncoh_blocks = h->mode == GPSACQ_MODE_GRID ? h->kblocks : 1;
     info->block_bytes = h->mode == GPSACQ_MODE_GRID ? h->block_bytes : h->chunk_bytes;
     info->max_acq = h->mode == GPSACQ_MODE_GRID ? h->cap_acq : 0;
@@ -787,19 +814,30 @@ int gpsacq_synchronize(gpsacq_t *h)
 
 // one (sub-)batch on the handle's stream; workspace slots [off, off + n_blocks)
 // (`timed`: record the stage events -- the last slice of a sliced host batch, see gpsacq_stage_times)
+// The batch is cut into launches of sub_blocks chunks (forward transform, cells, best-over-Doppler each): the block
+// spectra a forward launch writes (320 KB per chunk) are then still in the 126 MB L2 when the cell launch reads them,
+// instead of making a round trip through HBM as they do when thousands of chunks are transformed first.
+// Stage events bracket the LAST launch triple.
 static int search_device_impl(gpsacq *h, const uint8_t *d_bits, size_t n_blocks, const int32_t *d_sv, gpsacq_peak *d_out, size_t off,
                               bool last)
 {
-    if (last) CUDA_TRY(h, cudaEventRecord(h->ev[0], h->stream));
-    int rc = launch_fwd(h, 0, n_blocks, d_bits, h->d_xd + off * (size_t)h->n);
-    if (rc) return rc;
-    if (last) CUDA_TRY(h, cudaEventRecord(h->ev[1], h->stream));
-    rc = launch_cells(h, n_blocks, d_sv, off);
-    if (rc) return rc;
-    if (last) CUDA_TRY(h, cudaEventRecord(h->ev[2], h->stream));
-    best_kernel<<<(unsigned)((n_blocks + 3) / 4), 128, 0, h->stream>>>(h->d_cells + off * (size_t)h->ndop, d_sv, (int)n_blocks, h->ndop, h->dmax, h->w, (Peak *)d_out);
-    CUDA_TRY(h, cudaGetLastError());
-    if (last) CUDA_TRY(h, cudaEventRecord(h->ev[3], h->stream));
+    const size_t sub = (size_t)h->sub_blocks;
+    for (size_t done = 0; done < n_blocks; done += sub) {
+        const size_t n = std::min(sub, n_blocks - done), o = off + done;
+        const bool timed = last && done + n == n_blocks;
+        const int32_t *sv = d_sv ? d_sv + done : nullptr;
+        if (timed) CUDA_TRY(h, cudaEventRecord(h->ev[0], h->stream));
+        int rc = launch_fwd(h, 0, n, d_bits + done * (size_t)h->chunk_bytes, h->d_xd + o * (size_t)h->n);
+        if (rc) return rc;
+        if (timed) CUDA_TRY(h, cudaEventRecord(h->ev[1], h->stream));
+        rc = launch_cells(h, n, sv, o, (int)done);
+        if (rc) return rc;
+        if (timed) CUDA_TRY(h, cudaEventRecord(h->ev[2], h->stream));
+        best_kernel<<<(unsigned)((n + 3) / 4), 128, 0, h->stream>>>(h->d_cells + o * (size_t)h->ndop, sv, (int)n, h->ndop, h->dmax, h->w, (Peak *)d_out + done, (int)done);
+        CUDA_TRY(h, cudaGetLastError());
+        if (timed) CUDA_TRY(h, cudaEventRecord(h->ev[3], h->stream));
+        h->last_launch_blocks = (int)n;
+    }
     return GPSACQ_OK;
 }
 
@@ -926,7 +964,7 @@ int gpsacq_iq8_to_bits(gpsacq_t *h, const void *iq, size_t n_samples, int format
             if (n_samples > cap || done > 0)
                 if (cudaMemcpyAsync(d_iq, (const unsigned char *)iq + 2 * done, 2 * n, cudaMemcpyHostToDevice, h->stream) != cudaSuccess) { rc = GPSACQ_ECUDA; break; }
             const size_t nbytes = (n + 7) / 8;
-            iq8_to_bits_kernel<<<(unsigned)((nbytes + 255) / 256), 256, 0, h->stream>>>(d_iq, n, done, format, mi, mq, shift_hz, fs, d_bits);
+            if (iq8_convert_piece(h, d_iq, n, done, format, mi, mq, shift_hz, fs, d_bits) != GPSACQ_OK) { rc = GPSACQ_ECUDA; break; }
             if (cudaMemcpyAsync(bits_out + done / 8, d_bits, nbytes, cudaMemcpyDeviceToHost, h->stream) != cudaSuccess ||
                 cudaStreamSynchronize(h->stream) != cudaSuccess) { rc = GPSACQ_ECUDA; break; }
         }
@@ -935,6 +973,224 @@ int gpsacq_iq8_to_bits(gpsacq_t *h, const void *iq, size_t n_samples, int format
     cudaFree(d_iq); cudaFree(d_bits); cudaFree(d_sums);
     return rc;
 }
+
+}  // extern "C" (re-opened below)
+
+// ---- 8-bit IQ front-end with device buffers; exactly periodic phase table when fc/fs is a small rational ----------
+static bool small_rational(double x, unsigned long long &p, unsigned long long &q)
+{
+    // x = p/q with q <= 2^20, by continued fractions; accepted when |x - p/q| < 1e-15 * max(1, |x|)
+    if (!(x >= 0) || !(x < 1e6)) return false;
+    double a = x;
+    unsigned long long p0 = 0, q0 = 1, p1 = 1, q1 = 0;
+    for (int it = 0; it < 40; it++) {
+        const double fl = floor(a);
+        const unsigned long long ai = (unsigned long long)fl;
+        const unsigned long long p2 = ai * p1 + p0, q2 = ai * q1 + q0;
+        if (q2 > (1ull << 20)) break;
+        p0 = p1; q0 = q1; p1 = p2; q1 = q2;
+        if (fabs((double)p1 / (double)q1 - x) <= 1e-15 * std::max(1.0, x)) { p = p1 % q1; q = q1; return true; }
+        const double fr = a - fl;
+        if (fr < 1e-18) break;
+        a = 1.0 / fr;
+    }
+    return false;
+}
+
+static int iq8_convert_piece(gpsacq *h, const unsigned char *d_iq, size_t n, size_t n0, int format, double mi, double mq,
+                             double shift_hz, double fs, unsigned char *d_bits)
+{
+    const size_t nbytes = (n + 7) / 8;
+    unsigned long long p = 0, q = 0;
+    if (small_rational(fabs(shift_hz) / fs, p, q) && ((uintptr_t)d_iq % 16) == 0) {
+        if (h->iq_tab_q != q || h->iq_tab_p != p || h->iq_tab_neg != (shift_hz < 0)) {
+            std::vector<double> tab(2 * q);
+            for (unsigned long long k = 0; k < q; k++) {
+                const long double a = 2.0L * 3.14159265358979323846264338327950288L * (long double)k / (long double)q;
+                tab[2 * k] = (double)cosl(a); tab[2 * k + 1] = (double)(shift_hz < 0 ? -sinl(a) : sinl(a));
+            }
+            CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+            cudaFree(h->d_iq_tab); h->d_iq_tab = nullptr;
+            CUDA_TRY(h, cudaMalloc(&h->d_iq_tab, 2 * q * sizeof(double)));
+            CUDA_TRY(h, cudaMemcpy(h->d_iq_tab, tab.data(), 2 * q * sizeof(double), cudaMemcpyHostToDevice));
+            h->iq_tab_p = p; h->iq_tab_q = q; h->iq_tab_neg = shift_hz < 0;
+        }
+        iq8_to_bits_table_kernel<<<(unsigned)((nbytes + 255) / 256), 256, 0, h->stream>>>(d_iq, n, n0, format, mi, mq, (const double2 *)h->d_iq_tab, p, q, d_bits);
+    } else {
+        iq8_to_bits_kernel<<<(unsigned)((nbytes + 255) / 256), 256, 0, h->stream>>>(d_iq, n, n0, format, mi, mq, shift_hz, fs, d_bits);
+    }
+    CUDA_TRY(h, cudaGetLastError());
+    return GPSACQ_OK;
+}
+
+extern "C" int gpsacq_iq8_to_bits_device(gpsacq_t *h, const void *d_iq, size_t n_samples, int format, double shift_hz, double fs,
+                                         uint8_t *d_bits_out, void *d_sums)
+{
+    DeviceGuard guard;
+    if (!h || (!d_iq && n_samples) || (!d_bits_out && n_samples) || !d_sums || (format != GPSACQ_IQ_U8 && format != GPSACQ_IQ_S8) || !(fs > 0))
+        return GPSACQ_EINVAL;
+    if (n_samples == 0) return GPSACQ_OK;
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    long long sums[2];
+    CUDA_TRY(h, cudaMemsetAsync(d_sums, 0, 2 * sizeof(long long), h->stream));
+    iq8_sum_kernel<<<h->sm_count * 8, 256, 0, h->stream>>>((const unsigned char *)d_iq, n_samples, format, (long long *)d_sums);
+    CUDA_TRY(h, cudaGetLastError());
+    CUDA_TRY(h, cudaMemcpyAsync(sums, d_sums, sizeof sums, cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));               // the mean is a kernel argument of pass 2
+    return iq8_convert_piece(h, (const unsigned char *)d_iq, n_samples, 0, format, (double)sums[0] / (double)n_samples,
+                             (double)sums[1] / (double)n_samples, shift_hz, fs, d_bits_out);
+}
+
+// ---- the reverse converter: 1-bit real IF -> int8 IQ (c/conv_1bit_bin_to_hackrf_bin.cpp:29-86) -------------------------
+struct LoCycle { std::vector<unsigned char> tab; unsigned long long mu, lambda; };
+// The phase NCO of :33,:79-80 is a deterministic map on floats in [0,4): eventually periodic.  Brent's cycle search
+// (bounded), then the table of int(phase) -> lo_sin | lo_cos << 1 for the pre-period and one period.
+static bool conv_lo_cycle(double fc, double fs, unsigned long long n_needed, LoCycle &c)
+{
+    static const int lo_sin[4] = {1, 1, 0, 0}, lo_cos[4] = {1, 0, 0, 1};                  // :30-31
+    const float rate = (float)(4 * fc / fs);                                               // :33
+    auto step = [rate](float p) { p += rate; if (p >= 4) p -= 4; return p; };             // :79-80
+    const unsigned long long LIMIT = 1ull << 27;
+    unsigned long long power = 1, lam = 1;
+    float t = 0, hh = step(0.0f);
+    bool found = true;
+    while (memcmp(&t, &hh, sizeof t) != 0) {
+        if (power == lam) { t = hh; power *= 2; lam = 0; }
+        hh = step(hh); lam++;
+        if (lam > LIMIT) { found = false; break; }
+    }
+    unsigned long long mu = 0, len;
+    if (found) {
+        t = 0; hh = 0;
+        for (unsigned long long i = 0; i < lam; i++) hh = step(hh);
+        while (memcmp(&t, &hh, sizeof t) != 0) { t = step(t); hh = step(hh); mu++; if (mu > LIMIT) { found = false; break; } }
+    }
+    if (found) len = mu + lam;
+    else { if (n_needed > LIMIT) return false; mu = 0; lam = n_needed; len = n_needed; }   // no short cycle: the whole sequence
+    if (!(rate >= 0) || !(rate < 4)) return false;                                         // int(phase) would leave the 4-entry tables
+    c.tab.resize(len);
+    float ph = 0;
+    for (unsigned long long i = 0; i < len; i++) {
+        const int k = (int)ph;
+        c.tab[i] = (unsigned char)(lo_sin[k & 3] | (lo_cos[k & 3] << 1));
+        ph = step(ph);
+    }
+    c.mu = mu; c.lambda = lam;
+    return true;
+}
+
+struct ConvState { int device; double fc, fs; unsigned char *d_lo; LoCycle cyc; };
+static ConvState g_conv = {-1, 0, 0, nullptr, {}};
+
+static int conv_prepare(int device, double fc, double fs, unsigned long long n_needed)
+{
+    if (g_conv.d_lo && g_conv.device == device && g_conv.fc == fc && g_conv.fs == fs && g_conv.cyc.mu + g_conv.cyc.lambda >= std::min<unsigned long long>(n_needed, g_conv.cyc.mu + g_conv.cyc.lambda)) return GPSACQ_OK;
+    if (!(fs > 0) || !(fc >= 0) || !std::isfinite(fc) || !std::isfinite(fs)) { g_create_error = "bits_to_iq8: bad fc / fs"; return GPSACQ_EINVAL; }
+    LoCycle c;
+    if (!conv_lo_cycle(fc, fs, n_needed, c)) { g_create_error = "bits_to_iq8: 4*fc/fs must lie in [0,4) and the input be shorter than 2^27 samples when the LO recurrence has no short cycle"; return GPSACQ_EINVAL; }
+    if (g_conv.d_lo) { cudaFree(g_conv.d_lo); g_conv.d_lo = nullptr; }
+    if (cudaMalloc(&g_conv.d_lo, c.tab.size()) != cudaSuccess || cudaMemcpy(g_conv.d_lo, c.tab.data(), c.tab.size(), cudaMemcpyHostToDevice) != cudaSuccess) {
+        g_create_error = "bits_to_iq8: LO table upload failed"; return GPSACQ_ECUDA;
+    }
+    g_conv.device = device; g_conv.fc = fc; g_conv.fs = fs; g_conv.cyc = std::move(c);
+    return GPSACQ_OK;
+}
+
+extern "C" int gpsacq_bits_to_iq8_device(int device, const uint8_t *d_bits, size_t n_bytes, size_t first_sample, double fc, double fs,
+                                         int amplitude, int8_t *d_iq_out, void *cuda_stream)
+{
+    DeviceGuard guard;
+    if ((!d_bits && n_bytes) || (!d_iq_out && n_bytes) || amplitude < 0 || amplitude > 127) { g_create_error = "bits_to_iq8: bad arguments"; return GPSACQ_EINVAL; }
+    if (n_bytes == 0) return GPSACQ_OK;
+    if (device >= 0 && cudaSetDevice(device) != cudaSuccess) { g_create_error = "bits_to_iq8: cudaSetDevice failed (no CPU fallback)"; return GPSACQ_ECUDA; }
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) { g_create_error = "bits_to_iq8: no CUDA device (no CPU fallback)"; return GPSACQ_ECUDA; }
+    const int rc = conv_prepare(dev, fc, fs, first_sample + 8ull * n_bytes);
+    if (rc) return rc;
+    int sms = 148;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const size_t want = (n_bytes + 255) / 256;
+    const unsigned grid = (unsigned)std::min<size_t>(want, (size_t)sms * 16);
+    bits_to_iq8_kernel<<<grid, 256, 0, (cudaStream_t)cuda_stream>>>(d_bits, n_bytes, first_sample, g_conv.d_lo, g_conv.cyc.mu, g_conv.cyc.lambda, amplitude, (uint4 *)d_iq_out);
+    if (cudaGetLastError() != cudaSuccess) { g_create_error = "bits_to_iq8: kernel launch failed"; return GPSACQ_ECUDA; }
+    return GPSACQ_OK;
+}
+
+extern "C" int gpsacq_bits_to_iq8(int device, const uint8_t *bits, size_t n_bytes, size_t first_sample, double fc, double fs, int amplitude,
+                                  int8_t *iq_out)
+{
+    DeviceGuard guard;
+    if ((!bits && n_bytes) || (!iq_out && n_bytes)) { g_create_error = "bits_to_iq8: bad arguments"; return GPSACQ_EINVAL; }
+    if (n_bytes == 0) return GPSACQ_OK;
+    if (device >= 0 && cudaSetDevice(device) != cudaSuccess) { g_create_error = "bits_to_iq8: cudaSetDevice failed (no CPU fallback)"; return GPSACQ_ECUDA; }
+    // two pipeline slots: while slot k's output drains to the host, slot k^1 is converted
+    const size_t piece = (size_t)4 << 20;                 // 4 MiB of bits -> 64 MiB of IQ per slot
+    unsigned char *d_in[2] = {nullptr, nullptr}, *h_in[2] = {nullptr, nullptr};
+    int8_t *d_out[2] = {nullptr, nullptr}, *h_out[2] = {nullptr, nullptr};
+    cudaStream_t st[2] = {nullptr, nullptr};
+    int rc = GPSACQ_OK;
+    for (int k = 0; k < 2 && rc == GPSACQ_OK; k++) {
+        if (cudaStreamCreateWithFlags(&st[k], cudaStreamNonBlocking) != cudaSuccess || cudaMalloc(&d_in[k], piece) != cudaSuccess ||
+            cudaMalloc(&d_out[k], 16 * piece) != cudaSuccess || cudaMallocHost(&h_in[k], piece) != cudaSuccess ||
+            cudaMallocHost(&h_out[k], 16 * piece) != cudaSuccess) { g_create_error = "bits_to_iq8: allocation failed"; rc = GPSACQ_ENOMEM; }
+    }
+    size_t pending_off[2] = {0, 0}, pending_n[2] = {0, 0};
+    size_t done = 0;
+    for (int it = 0; rc == GPSACQ_OK && (done < n_bytes || pending_n[0] || pending_n[1]); it++) {
+        const int k = it & 1;
+        if (pending_n[k]) {                                // drain what this slot produced two iterations ago
+            if (cudaStreamSynchronize(st[k]) != cudaSuccess) { g_create_error = "bits_to_iq8: stream failed"; rc = GPSACQ_ECUDA; break; }
+            memcpy(iq_out + 16 * pending_off[k], h_out[k], 16 * pending_n[k]);
+            pending_n[k] = 0;
+        }
+        if (done < n_bytes) {
+            const size_t n = std::min(piece, n_bytes - done);
+            memcpy(h_in[k], bits + done, n);
+            if (cudaMemcpyAsync(d_in[k], h_in[k], n, cudaMemcpyHostToDevice, st[k]) != cudaSuccess) { g_create_error = "bits_to_iq8: H2D failed"; rc = GPSACQ_ECUDA; break; }
+            rc = gpsacq_bits_to_iq8_device(-1, d_in[k], n, first_sample + 8 * done, fc, fs, amplitude, d_out[k], st[k]);
+            if (rc) break;
+            if (cudaMemcpyAsync(h_out[k], d_out[k], 16 * n, cudaMemcpyDeviceToHost, st[k]) != cudaSuccess) { g_create_error = "bits_to_iq8: D2H failed"; rc = GPSACQ_ECUDA; break; }
+            pending_off[k] = done; pending_n[k] = n;
+            done += n;
+        }
+    }
+    for (int k = 0; k < 2; k++) {
+        if (st[k]) { cudaStreamSynchronize(st[k]); cudaStreamDestroy(st[k]); }
+        cudaFree(d_in[k]); cudaFree(d_out[k]); cudaFreeHost(h_in[k]); cudaFreeHost(h_out[k]);
+    }
+    return rc;
+}
+
+// ---- gps_sig_gen.m, literally --------------------------------------------------------------------------------------
+extern "C" int gpsacq_sig_gen_literal(int device, int prn, const uint8_t *nav_bits01, int n_nav_bits, uint8_t *bits_out, void *d_bits_out)
+{
+    DeviceGuard guard;
+    if (prn < 1 || prn > 32 || !nav_bits01 || n_nav_bits < 1 || n_nav_bits > (1 << 20) || (!bits_out && !d_bits_out)) {
+        g_create_error = "gpsacq_sig_gen_literal: bad arguments"; return GPSACQ_EINVAL;
+    }
+    if (device >= 0 && cudaSetDevice(device) != cudaSuccess) { g_create_error = "gpsacq_sig_gen_literal: cudaSetDevice failed (no CPU fallback)"; return GPSACQ_ECUDA; }
+    const long long n_data = (long long)n_nav_bits * SIGLIT_PER_BIT, n_out = n_data + SIGLIT_TAPS - 1;
+    const size_t nbytes = (size_t)((n_out + 7) / 8);
+    const double ca_rate = 1.023e6 * SIGLIT_OV, fc = ca_rate / 4;                          // gps_sig_gen.m:8-9,14,34
+    const double two_pi_fc = (2.0 * 3.141592653589793) * fc, inv_rate = 1.0 / ca_rate;     // 2.*pi.*fc ... .*(1./ca_rate), left to right
+    unsigned char *d_nav = nullptr, *d = (unsigned char *)d_bits_out;
+    bool own = false;
+    cudaError_t e = cudaMalloc(&d_nav, (size_t)n_nav_bits);
+    if (e == cudaSuccess) e = cudaMemcpy(d_nav, nav_bits01, (size_t)n_nav_bits, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess && !d) { e = cudaMalloc(&d, nbytes); own = e == cudaSuccess; }
+    if (e == cudaSuccess) {
+        sig_gen_literal_kernel<<<(unsigned)((nbytes + 255) / 256), 256>>>(kTaps[prn - 1][0], kTaps[prn - 1][1], d_nav, n_data, n_out, two_pi_fc, inv_rate, d);
+        e = cudaGetLastError();
+    }
+    if (e == cudaSuccess && bits_out) e = cudaMemcpy(bits_out, d, nbytes, cudaMemcpyDeviceToHost);
+    if (e == cudaSuccess) e = cudaDeviceSynchronize();
+    cudaFree(d_nav);
+    if (own) cudaFree(d);
+    if (e != cudaSuccess) { g_create_error = std::string("gpsacq_sig_gen_literal: ") + cudaGetErrorString(e); return GPSACQ_ECUDA; }
+    return GPSACQ_OK;
+}
+
+extern "C" {
 
 int gpsacq_synth_capture(int device, double fs, double fc, const gpsacq_sat *sats, int n_sats, double noise_sigma,
                          double nav_bps, uint64_t seed, size_t n_samples, uint8_t *bits_out, void *d_bits_out)

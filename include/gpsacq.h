@@ -143,9 +143,13 @@ typedef struct gpsacq_info {
     double  doppler_step;  /* Hz between Doppler bins (REF: FS/fft_len)            */
     int32_t dop_first;     /* GRID: first bin of this handle's shard (0 = bin -dmax); n_doppler = bins in the shard */
     int32_t n_doppler_full;/* bins of the whole grid, 2*dmax+1                                    */
+    int32_t blocks_per_launch; /* REF: chunks per kernel launch of the most recent batch (a batch is cut into launches
+                              of GPSACQ_SUB_BLOCKS = 128 chunks so that the block spectra stay in L2); 0 in GRID mode */
+    int32_t reserved;
 } gpsacq_info;
 
-/* Number of kernels this library launches for a batch (for bench.py's gpu_launches). */
+/* Kernels launched per launch triple (forward transform, cells, best over Doppler); a REF batch of n chunks is
+ * ceil(n / blocks_per_launch) triples (for bench.py's gpu_launches). */
 #define GPSACQ_LAUNCHES_PER_BATCH 3
 
 int  gpsacq_create(const gpsacq_cfg *cfg, gpsacq_t **out);
@@ -187,6 +191,23 @@ int  gpsacq_acquire_device(gpsacq_t *h, const uint8_t *d_packed_bits, size_t n_a
 #define GPSACQ_IQ_S8 1
 int  gpsacq_iq8_to_bits(gpsacq_t *h, const void *iq, size_t n_samples, int format, double shift_hz,
                         double fs, uint8_t *bits_out);
+
+/* The same front-end with device-resident buffers, asynchronous on the handle's stream (d_iq: 2*n_samples bytes,
+ * d_bits_out: ceil(n_samples/8) bytes, d_sums: 16 bytes of scratch).  For captures that fit in device memory. */
+int  gpsacq_iq8_to_bits_device(gpsacq_t *h, const void *d_iq, size_t n_samples, int format, double shift_hz,
+                               double fs, uint8_t *d_bits_out, void *d_sums);
+
+/* The reverse converter (c/conv_1bit_bin_to_hackrf_bin.cpp:29-86): packed 1-bit real-IF samples -> interleaved int8
+ * I,Q at baseband for HackRF replay.  I = A*Bipolar(bit ^ lo_sin[int(phase)]), Q = A*Bipolar(bit ^ lo_cos[int(phase)]),
+ * lo_sin = {1,1,0,0}, lo_cos = {1,0,0,1}, Bipolar(1) = -A (the reference's A is 30); the float phase NCO advances by
+ * (float)(4*fc/fs) per sample, wraps at 4 and runs on over the WHOLE input (:33,:79-80).  n_bytes input bytes ->
+ * 16*n_bytes output bytes.  first_sample: index of the input's first sample in the stream (0 for a whole file), so a
+ * long file can be converted in pieces.  Host buffers (pipelined H2D / kernel / D2H); `_device`: device buffers,
+ * asynchronous on `cuda_stream` (NULL: the default stream). */
+int  gpsacq_bits_to_iq8(int device, const uint8_t *packed_bits, size_t n_bytes, size_t first_sample, double fc, double fs,
+                        int amplitude, int8_t *iq_out);
+int  gpsacq_bits_to_iq8_device(int device, const uint8_t *d_packed_bits, size_t n_bytes, size_t first_sample, double fc,
+                               double fs, int amplitude, int8_t *d_iq_out, void *cuda_stream);
 
 /* ---- several GPUs in one process ------------------------------------------------------------------
  * One engine per device.  REF mode: a batch's chunks are split into contiguous ranges (chunk b keeps PRN
@@ -269,6 +290,13 @@ typedef struct gpsacq_sat {
 } gpsacq_sat;
 int  gpsacq_synth_capture(int device, double fs, double fc, const gpsacq_sat *sats, int n_sats, double noise_sigma,
                           double nav_bps, uint64_t seed, size_t n_samples, uint8_t *bits_out, void *d_bits_out);
+
+/* gps_sig_gen.m, literally (gps_sig_gen.m:8-41 with cacode.m): one satellite, chips zero-stuffed x8 to 8.184 Msps, 20
+ * code periods per NAV bit, 49-tap rcosine(1,8) FIR, carrier at fs/4, sign, 'ubit1' -- the chain that wrote the
+ * reference's bundled gps_sig_tmp.bin (PRN 8).  nav_bits01: n_nav_bits values 0/1 (the script draws them with rand;
+ * data = 1 - 2*bit).  Writes ceil((n_nav_bits*163680 + 48)/8) bytes to bits_out (host) and/or d_bits_out (device).
+ * Double precision with MATLAB's operation order: with the file's own NAV bits the output equals the file bit for bit. */
+int  gpsacq_sig_gen_literal(int device, int prn, const uint8_t *nav_bits01, int n_nav_bits, uint8_t *bits_out, void *d_bits_out);
 
 /* Elapsed milliseconds of the stages of the most recent batch, measured with CUDA
  * events on the launching stream: [0] unpack+mix+forward FFT kernel, [1] cell kernel

@@ -64,6 +64,8 @@ def _lib() -> C.CDLL:
     lib.oracle_grid_acquire.argtypes = [vp, vp, vp, vp, vp, vp]
     lib.oracle_grid_acquire_svs.restype = C.c_int
     lib.oracle_grid_acquire_svs.argtypes = [vp, vp, vp, C.c_int, vp, vp, vp, vp]
+    lib.oracle_conv_1bit_iq8.argtypes = [vp, C.c_size_t, C.c_size_t, C.c_double, C.c_double, C.c_int, vp]
+    lib.oracle_sig_gen_literal.argtypes = [C.c_int, vp, C.c_int, vp, vp]
     return lib
 
 
@@ -201,6 +203,44 @@ class GridOracle:
         return (out, cells) if want_cells else out
 
 
+def conv_1bit_iq8(bits, fc: float, fs: float, amp: int = 30, first_sample: int = 0) -> np.ndarray:
+    """c/conv_1bit_bin_to_hackrf_bin.cpp:29-86 restated: packed 1-bit IF -> interleaved int8 I,Q."""
+    buf = np.ascontiguousarray(np.frombuffer(bits, np.uint8) if not isinstance(bits, np.ndarray) else bits)
+    out = np.zeros(16 * buf.size, np.int8)
+    lib().oracle_conv_1bit_iq8(buf.ctypes.data, buf.size, first_sample, fc, fs, amp, out.ctypes.data)
+    return out
+
+
+def rcosine_1_8() -> np.ndarray:
+    """MATLAB rcosine(1, 8): normal raised-cosine FIR, roll-off 0.5, delay 3 -> 49 taps, in double."""
+    n = np.arange(-24, 25) / 8.0
+    with np.errstate(divide="ignore", invalid="ignore"):
+        h = np.sinc(n) * np.cos(np.pi * 0.5 * n) / (1 - n ** 2)
+    h[np.isclose(np.abs(n), 1)] = np.pi / 4 * np.sinc(1.0)
+    return h
+
+
+def sig_gen_literal(sv: int, nav01) -> np.ndarray:
+    """gps_sig_gen.m:8-41 restated (see gpsacq_oracle.c): the packed 'ubit1' bytes for satellite index sv (PRN-1)."""
+    nav = np.ascontiguousarray(nav01, np.uint8)
+    n_out = nav.size * 163680 + 48
+    out = np.zeros((n_out + 7) // 8, np.uint8)
+    taps = np.ascontiguousarray(rcosine_1_8(), np.float64)
+    lib().oracle_sig_gen_literal(sv, nav.ctypes.data, nav.size, taps.ctypes.data, out.ctypes.data)
+    return out
+
+
+def recover_nav_bits(file_bits: np.ndarray, sv: int) -> np.ndarray:
+    """The NAV bits gps_sig_gen.m drew with rand, read back from the file it wrote: the sign of each 20 ms stretch
+    against a generation with all-zero NAV bits."""
+    n = file_bits.size * 8 // 163680
+    ref = np.unpackbits(sig_gen_literal(sv, np.zeros(n, np.uint8)), bitorder="little")[24: 24 + n * 163680]
+    got = np.unpackbits(file_bits, bitorder="little")[24: 24 + n * 163680]
+    agree = (ref == got).reshape(n, 163680).mean(1)
+    assert np.all(np.abs(agree - 0.5) > 0.4), "file is not a gps_sig_gen.m product for this satellite"
+    return (agree < 0.5).astype(np.uint8)
+
+
 def mkl_env() -> dict:
     """Environment that makes the fftw3.h stand-in use MKL (exported by torch's libtorch_cpu.so)."""
     env = dict(os.environ)
@@ -282,10 +322,70 @@ class RefHarness:
         return self._l.ref_search_code(sv, g1)
 
 
-# ---- consumers of the acquisition records: plain-Python restatements ----------------
-# PARITY UNPINNED for these two: c/channel.cpp and c/search.cpp need the receiver's FPGA/SPI layer and cannot be built
-# or run here; the restatements follow the cited lines, and the per-chunk Sample()+Correlate() they call is the pinned
-# oracle above.
+# ---- consumers of the acquisition records -----------------------------------------------
+# The receiver's own c/search.cpp + c/channel.cpp, UNMODIFIED, run here behind a stand-in for their SPI / coroutine /
+# clock layer (ref_target_harness.cpp -> oracle/_ref/libref_target.so): RefTarget below.  Its event log
+# (tests/golden/ref_target_events.json, made by tests/golden/make_golden_target.py) pins the plain-Python
+# restatements that follow, and through them -- and directly -- the engine's hand-off and service loop.
+SPI_CMDS = ("CmdSample", "CmdSetMask", "CmdSetRateCA", "CmdSetRateLO", "CmdSetGainCA", "CmdSetGainLO", "CmdSetSV", "CmdPause",
+            "CmdSetVCO", "CmdGetSamples", "CmdGetChan", "CmdGetClocks", "CmdGetGlitches", "CmdSetDAC", "CmdSetLCD", "CmdGetJoy")   # c/spi.h:9-26
+
+
+class RefTarget:
+    """One run of the receiver's SearchTask() + 12 ChanTask()s (the reference's own code) over a chunk stream.
+    One instance per process.  fc / fs are the macros of c/gps.h (2.6 MHz / 10 MHz)."""
+
+    def __init__(self):
+        p = HERE / "_ref" / "libref_target.so"
+        if not p.exists():
+            raise FileNotFoundError(f"{p}: build with `make -C oracle` where /root/reference exists")
+        self._l = C.CDLL(str(p))
+        self._l.reft_fc.restype = C.c_double
+        self._l.reft_fs.restype = C.c_double
+        self._l.reft_run.argtypes = [C.c_void_p, C.c_size_t, C.c_uint, C.c_void_p, C.c_int]
+        self.fc, self.fs, self.num_chans = self._l.reft_fc(), self._l.reft_fs(), self._l.reft_num_chans()
+
+    def run(self, bits, us_per_yield: int = 2000, max_rec: int = 1 << 16):
+        """Returns the parsed event list: dicts {"type": "start", chunk, ch, sv, taps, lo_shift, ca_shift, secs, lo_rate,
+        ca_rate, ca_pause, mask} and {"type": "lost", chunk, ch, sv, mask} in the order they happened."""
+        buf = np.ascontiguousarray(np.frombuffer(bits, np.uint8) if not isinstance(bits, np.ndarray) else bits)
+        rec = np.zeros((max_rec, 8), np.int32)
+        n = self._l.reft_run(buf.ctypes.data, buf.size, us_per_yield, rec.ctypes.data, max_rec)
+        if n < 0 or n > max_rec:
+            raise RuntimeError(f"reft_run returned {n}")
+        return parse_target_log(rec[:n])
+
+
+def parse_target_log(rec) -> list:
+    """One pass over the log.  CHANNEL::Start() (c/channel.cpp:134-171) spans a TimerWait(3) during which other tasks run,
+    so what it sends is matched by channel number: CmdSetRateLO / CmdSetRateCA / CmdPause / CmdSetSV with wparam == ch
+    up to the CmdSetMask that sets the channel's bit; a CmdSetMask that clears bits is CHANNEL::SignalLost() (:245-249)."""
+    events, mask, sv_of_ch, pending = [], 0, {}, {}
+    for r in rec:
+        kind, chunk, a, b, c, d, e, u = (int(v) for v in r)
+        u &= 0xFFFFFFFF
+        if kind == 0:                                   # ChanStart(ch, sv, t_sample, taps, lo_shift, ca_shift)
+            ev = dict(type="start", chunk=chunk, ch=a, sv=b, taps=c, lo_shift=d, ca_shift=e, secs=u / 1e6, ca_pause=0)
+            pending[a] = ev
+            sv_of_ch[a] = b
+            events.append(ev)
+            continue
+        name, w = SPI_CMDS[a], b
+        if name == "CmdSetMask":
+            for ch in range(32):
+                if (mask >> ch) & 1 and not (w >> ch) & 1:
+                    events.append(dict(type="lost", chunk=chunk, ch=ch, sv=sv_of_ch.get(ch, -1), mask=w))
+            for ch in list(pending):
+                if (w >> ch) & 1:
+                    pending.pop(ch)["mask"] = w
+            mask = w
+        elif w in pending:
+            ev = pending[w]
+            if name == "CmdSetRateLO": ev["lo_rate"] = u
+            elif name == "CmdSetRateCA": ev["ca_rate"] = u
+            elif name == "CmdPause": ev["ca_pause"] = u + 1                      # spi_set(CmdPause, ch, ca_pause-1), :165
+            elif name == "CmdSetSV": ev["taps_sent"] = u
+    return events
 L1_HZ = 1575.42e6          # c/gps.h:22
 CPS_HZ = 1.023e6           # c/gps.h:25
 SATS_TAPS = [(2, 6), (3, 7), (4, 8), (5, 9), (1, 9), (2, 10), (1, 8), (2, 9), (3, 10), (2, 3), (3, 4), (5, 6), (6, 7),

@@ -124,3 +124,38 @@ def compare_runs(got_runs, ref_runs):
                 assert s <= 25.0 + 0.05, f"run {r['run']} sv {sv} detected on one side only with SNR {s}"
         assert len(g["all_snr"]) == 32
         assert max(abs(a - b) for a, b in zip(g["all_snr"], r["all_snr"])) <= 1.0
+
+
+# ---- the receiver's own search loop + hand-off (tests/golden/ref_target_events.json, made from the UNMODIFIED
+# c/search.cpp + c/channel.cpp by tests/golden/make_golden_target.py) ---------------------------------------------------
+def target_golden():
+    import hashlib
+    import importlib
+    import json
+    g = json.loads((GOLD / "ref_target_events.json").read_text())
+    import gpsacq_loader
+    gpsacq_loader.load()
+    sg = importlib.import_module("gnss_gps_sdr_b200.siggen")
+    i = g["input"]
+    sats = sg.default_constellation(i["fs"], cn0_dbhz=i["cn0_dbhz"], seed=i["seed_constellation"])
+    bits = sg.synth_capture(40960 * i["n_chunks"], i["fs"], i["fc"], sats, seed=i["seed_noise"])
+    assert hashlib.sha256(bits.tobytes()).hexdigest() == i["sha256"], "the numpy generator no longer reproduces the golden's input"
+    return g, bits
+
+
+def replay_target(g, bits, feed_chunk, signal_lost):
+    """Feed the stream chunk by chunk; after chunk c apply the losses the reference logged while chunk c was its most
+    recently sampled one (CHANNEL::SignalLost(): channel freed, SearchEnable(sv)).  feed_chunk(bytes) -> list of
+    (sv, ch, lo_shift, ca_shift, record) for the detections of that chunk; signal_lost(ch, sv).
+    Returns [(chunk, sv, ch, lo_shift, ca_shift, record)], to be compared with the golden's start events."""
+    lost_after = {}
+    for e in g["events"]:
+        if e["type"] == "lost":
+            lost_after.setdefault(e["chunk"], []).append(e)
+    got = []
+    for c in range(g["input"]["n_chunks"]):
+        for (sv, ch, lo, ca, rec) in feed_chunk(bits[c * 5120:(c + 1) * 5120].tobytes()):
+            got.append((c, sv, ch, lo, ca, rec))
+        for e in lost_after.get(c, []):
+            signal_lost(e["ch"], e["sv"])
+    return got

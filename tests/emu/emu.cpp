@@ -35,10 +35,12 @@ static void emu_cell_sub(int s, int s_next, const cf *xd_blk, const cf *cext_sv,
 }
 
 template <class G>
-static void emu_cell_t(const cf *xd_blk, const cf *cext_sv, int dop, int wlen, cf *y, float *best, int *besti, float *sum)
+static void emu_cell_t(const cf *xd_blk, const cf *cext_sv, int dop, int wlen, cf *y, float *best, int *besti, float *sum, int seg = -1)
 {
     constexpr int NW = G::RC;
-    std::vector<cf> tw = make_tw(G::N), ktab = make_ktab<G>();
+    // seg >= 0: output segment `seg` of the window (cell_kernel_tm<..., SEG = true>): its own ktab, window shortened by seg*N2
+    std::vector<cf> tw = make_tw(G::N), ktab = seg >= 0 ? make_ktab_seg<G>(seg) : make_ktab<G>();
+    if (seg > 0) wlen -= seg * G::N2;
     std::vector<cf> sm((size_t)G::SMEM_ELEMS);
     std::vector<cf> acc((size_t)G::NC * NW, mk(0, 0));
     if constexpr (G::ROT) {
@@ -189,6 +191,14 @@ int emu_cell(int id, const float *xd_blk, const float *cext_sv, int dop, int wle
 }
 
 // x: W complex time samples; out: W spectral values in the cell's (a,b,c)-linear order (conjugated if conj)
+// one output segment of a window longer than N2 (REF mode above 10 MHz): geometry 4 x 10000 only
+int emu_cell_seg(int seg, const float *xd_blk, const float *cext_sv, int dop, int wlen, float *y, float *best, int *besti, float *sum)
+{
+    emu_cell_t<Geom<4, 25, 20, 20> >((const cf *)xd_blk, (const cf *)cext_sv, dop, wlen, (cf *)y, best, besti, sum, seg);
+    *besti += seg * 10000;
+    return 0;
+}
+
 int emu_pfa_fwd(int w, const float *x, int conj, float *out)
 {
     switch (w) {

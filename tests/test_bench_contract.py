@@ -53,4 +53,6 @@ def test_gpu_arm_line_has_the_contract_keys():
             assert k in d, k
     rf = d["roofline"]
     assert rf["bound"] == "hbm" and rf["unit"] == "GB/s" and abs(rf["frac"] - rf["achieved"] / rf["peak"]) < 1e-9
-    assert d["gpu_launches"] == 3 * d["steps"] and d["e2e"]["h2d_bytes_per_step"] > 0 and d["clocks"]["sm_mhz"] > 0
+    assert d["gpu_launches"] == 3 * rf["launches_per_step"] * d["steps"] and d["e2e"]["h2d_bytes_per_step"] > 0 and d["clocks"]["sm_mhz"] > 0
+    assert 0 < rf["fp32_frac"] < 1 and rf["fp32_peak_tflops"] == 74.4 and rf["traffic"] > 0
+    assert d["ms_per_step"] * d["steps"] >= 150            # 3 steps of ~60 ms: the default 40 steps run for seconds

@@ -240,10 +240,33 @@ def test_batching_and_ragged_sizes(ga, engines):
 
 
 def test_rejects_unsupported_configs(ga):
-    with pytest.raises(ga.GpsAcqError, match="not supported"):
-        ga.Acquisition(4e6, 16.368e6)
+    with pytest.raises(ga.GpsAcqError, match="fft_len"):
+        ga.Acquisition(4e6, 40.5e6)                 # FS/1000 > FFT_LEN: the reference's window would run past its buffer
     with pytest.raises(ga.GpsAcqError):
         ga.Acquisition(4e6, -1.0)
+
+
+# ---- sampling rates above 10 MHz: W > 10000, search window covered by output segments (c/search_offline.cpp:190 takes any
+# FS with FS/1000 <= FFT_LEN; a 16.368 MHz front-end is the common case) -----------------------------------------------
+@pytest.mark.parametrize("fs,fc,seed", [(16.368e6, 4.092e6, 13), (25e6, 6.25e6, 14), (40e6, 10e6, 15)])
+def test_high_sampling_rates_vs_oracle(engines, oracle_mod, siggen, fs, fc, seed):
+    sats = siggen.default_constellation(fs, cn0_dbhz=57.0, seed=seed)
+    bits = siggen.synth_capture(40960 * 32, fs, fc, sats, seed=seed)
+    acq = engines(fc, fs)
+    W = int(np.ceil(fs / 1000))
+    assert acq.info["window"] == W and acq.info["n2"] == 10000 and acq.n_doppler == 2 * int(5000.0 * 40000 / fs) + 1
+    got = acq.search_blocks(bits)
+    o = oracle_mod.Oracle(fc, fs)
+    ref = o.search_blocks(bits)
+    compare_peaks(got, ref)
+    assert (ref["snr"] >= 25).sum() >= 6            # (the coherent window shrinks with FS: 40000 samples are 1 ms at 40 MHz)
+    for b in (0, 20):                               # per-cell statistics over the whole window (all segments merged)
+        cs = acq.cell_stats(b)
+        mp, mi, tp = o.cells(bits[b * 5120:(b + 1) * 5120], b)
+        assert np.abs(cs["max_pwr"] / mp - 1).max() <= 2e-5 and np.abs(cs["tot_pwr"] / tp - 1).max() <= 2e-5
+        assert (cs["max_idx"] != mi).sum() <= 1
+    for sv in (0, 31):
+        assert np.array_equal(acq.replica_time(sv).view(np.uint32), oracle_mod.replica_time(fs, sv).view(np.uint32))
 
 
 # ---- other sampling rates, synthetic captures (no reference fixture exists) --------------------------------

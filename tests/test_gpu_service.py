@@ -1,8 +1,9 @@
 """the consumers of the acquisition records.
 
-  * hand-off arithmetic of CHANNEL::Start() (c/channel.cpp:134-171) -- CPU, bit-exact against the oracle restatement
-  * the receiver's SearchTask() loop (c/search.cpp:214-239) over the capture fixture -- GPU, batched and speculative,
-    must produce exactly the events of the oracle's one-chunk-at-a-time loop
+  * hand-off arithmetic of CHANNEL::Start() (c/channel.cpp:134-171) -- CPU, bit-exact against the words the reference's own
+    CHANNEL::Start() sent (golden run of the unmodified c/channel.cpp) and against the oracle restatement
+  * the receiver's SearchTask() loop (c/search.cpp:214-239) -- GPU, batched and speculative: replays the golden run of the
+    unmodified c/search.cpp + c/channel.cpp event for event, and equals the oracle's one-chunk-at-a-time loop on the capture
 """
 import numpy as np
 import pytest
@@ -29,6 +30,50 @@ def test_handoff_matches_channel_start(ga, oracle_mod):
     # the receiver's own numbers (FS = 10 MHz, FC = 2.6 MHz, 250 Hz bins): +4 bins = +1 kHz
     h = oracle_mod.channel_start(0, 4, 1234, 2.6e6, 10e6, 40000, 0.0)
     assert h["lo_dop_hz"] == 1000.0 and h["ca_pause"] == (20000 - 1234) % 10000 and h["taps"] == (2 << 4) + 6
+
+
+def test_handoff_vs_the_reference_log(ga):
+    """gpsacq_handoff_compute() against what the reference's own CHANNEL::Start() (UNMODIFIED c/channel.cpp, run behind
+    oracle/ref_target_harness.cpp) sent to the FPGA for every ChanStart() of the golden run: carrier / code NCO words,
+    code-generator pause (after the code creep over the logged 1.118 s), tap word.  Host code: needs no GPU."""
+    from conftest import GOLD
+    import json
+    g = json.loads((GOLD / "ref_target_events.json").read_text())
+    starts = [e for e in g["events"] if e["type"] == "start" and "mask" in e]
+    assert len(starts) >= 25
+    for e in starts:
+        peak = np.zeros(1, ga.PEAK_DTYPE)[0]
+        peak["sv"], peak["lo_shift"], peak["ca_shift"], peak["snr"] = e["sv"], e["lo_shift"], e["ca_shift"], 30.0
+        h = ga.handoff(peak, g["input"]["fc"], g["input"]["fs"], g["input"]["fs"], g["fft_len"], e["secs"])
+        assert (int(h["lo_rate"]), int(h["ca_rate"]), int(h["ca_pause"]), int(h["taps"])) == (e["lo_rate"], e["ca_rate"], e["ca_pause"], e["taps"]), e
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("max_rounds", [1, 0])
+def test_service_loop_vs_the_reference_log(ga, max_rounds):
+    """gpsacq_service_* replays the golden run of the receiver's own SearchTask() + ChanTask()s (UNMODIFIED c/search.cpp and
+    c/channel.cpp): 29 detections handed to the same channels on the same chunks with the same bins, across 25 signal
+    losses (CHANNEL::SignalLost() -> channel freed, SearchEnable(sv)) and the re-acquisitions that follow."""
+    from conftest import target_golden, replay_target
+    g, bits = target_golden()
+    with ga.Acquisition(g["input"]["fc"], g["input"]["fs"]) as acq:
+        svc = ga.SearchService(acq, num_chans=12, max_rounds_per_batch=max_rounds)
+
+        def feed(chunk):
+            used, ev = svc.feed(chunk)
+            assert used == 1
+            return [(int(e["sv"]), int(e["ch"]), int(e["peak"]["lo_shift"]), int(e["peak"]["ca_shift"]), e) for e in ev]
+
+        def lost(ch, sv):
+            svc.signal_lost(ch)
+            svc.enable(sv)
+
+        got = replay_target(g, bits, feed, lost)
+        svc.close()
+    want = [(e["chunk"], e["sv"], e["ch"], e["lo_shift"], e["ca_shift"]) for e in g["events"] if e["type"] == "start"]
+    assert [x[:5] for x in got] == want
+    for x in got:
+        assert int(x[5]["chunk_index"]) == x[0] and int(x[5]["start"]["taps"]) == next(e["taps"] for e in g["events"] if e["type"] == "start" and e["chunk"] == x[0])
 
 
 def _events_equal(ev, want):

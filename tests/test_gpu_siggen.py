@@ -36,3 +36,33 @@ def test_gpu_generator_argument_checks(ga):
     with pytest.raises(ga.GpsAcqError):
         ga.synth_capture_gpu(64, 5.456e6, 4.092e6, [dict(prn=40, amp=1.0, doppler_hz=0.0, code_phase_chips=0.0)])
     assert ga.synth_capture_gpu(0, 5.456e6, 4.092e6, []).size == 0
+
+
+# ---- gps_sig_gen.m, literally: pinned by the reference's own bundled file -------------------------------------------
+def test_sig_gen_literal_reproduces_the_bundled_file(ga, oracle_mod):
+    """gpsacq_sig_gen_literal(PRN 8, the NAV bits of gps_sig_tmp.bin) == the reference's gps_sig_tmp.bin, bit for bit:
+    SHA-256 of all 2,046,006 bytes, and byte equality with the committed fixture (its first 327,680 bytes).
+    Another PRN / other NAV bits against the oracle restatement of gps_sig_gen.m:8-41."""
+    import hashlib, json
+    from conftest import CAPTURES, GOLD
+    g = json.loads((GOLD / "f1f2_golden.json").read_text())["gps_sig_gen"]
+    out = ga.sig_gen_literal(g["prn"], g["nav_bits01"])
+    fx = CAPTURES["gps_sig"]["bin"].read_bytes()
+    assert out[: len(fx)].tobytes() == fx
+    assert out.size == g["n_bytes"] and hashlib.sha256(out.tobytes()).hexdigest() == g["sha256_file"]
+    nav = np.random.default_rng(5).integers(0, 2, 7).astype(np.uint8)
+    assert np.array_equal(ga.sig_gen_literal(23, nav), oracle_mod.sig_gen_literal(22, nav))
+    with pytest.raises(ga.GpsAcqError):
+        ga.sig_gen_literal(33, nav)
+
+
+def test_sig_gen_literal_is_found_where_the_reference_finds_it(ga):
+    """gps_test on gps_sig_tmp.bin reports sv 7 at lo_shift 0, ca_shift 260 (run 0) -- the generated
+    file searched by the engine gives the same."""
+    import json
+    from conftest import GOLD
+    g = json.loads((GOLD / "f1f2_golden.json").read_text())["gps_sig_gen"]
+    bits = ga.sig_gen_literal(g["prn"], g["nav_bits01"][:3])[: 32 * 5120]
+    with ga.Acquisition(2.046e6, 8.184e6) as acq:
+        p = acq.search_blocks(bits)[7]
+    assert (int(p["lo_shift"]), int(p["ca_shift"])) == (0, 260) and p["snr"] > 500

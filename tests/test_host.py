@@ -182,6 +182,32 @@ def test_kernel_math_replay_matches_numpy(gid, W):
         assert abs(best.value / pw.max() - 1) < 1e-5 and abs(sm.value / pw.sum() - 1) < 1e-5
 
 
+def test_segmented_window_replay_matches_numpy():
+    """Sampling rates above 10 MHz: the W > 10000 search window is covered by output segments of the 4 x 10000 geometry
+    (ga_kernels.cuh c_ktab_seg).  Replay of every segment against the full 40000-point backward FFT."""
+    L = _emu()
+    fp = ctypes.POINTER(ctypes.c_float)
+    P = lambda a: a.ctypes.data_as(fp)
+    N1, N2, N, W = 4, 10000, 40000, 36368
+    rng = np.random.default_rng(44)
+    Xs = (rng.standard_normal(N) + 1j * rng.standard_normal(N)).astype(np.complex64)
+    Cc = (rng.standard_normal(N) + 1j * rng.standard_normal(N)).astype(np.complex64)
+    xd = np.conj(Xs).reshape(N2, N1).T.copy()
+    cd = Cc.reshape(N2, N1).T
+    cext = np.concatenate([cd, cd], axis=1).copy()
+    for dop in (-12, 0, 7):
+        y = np.fft.ifft(np.conj(Xs.astype(np.complex128)) * np.roll(Cc.astype(np.complex128), dop)) * N
+        for seg in range(4):
+            yy = np.zeros(N2, np.complex64)
+            best, bi, sm = ctypes.c_float(), ctypes.c_int(), ctypes.c_float()
+            L.emu_cell_seg(seg, P(xd.view(np.float32)), P(cext.view(np.float32)), dop, W, P(yy.view(np.float32)),
+                           ctypes.byref(best), ctypes.byref(bi), ctypes.byref(sm))
+            assert np.abs(yy - y[seg * N2:(seg + 1) * N2]).max() <= 2e-6 * np.abs(y).max()
+            pw = np.abs(y[seg * N2:min(W, (seg + 1) * N2)]) ** 2
+            assert bi.value == seg * N2 + int(pw.argmax())
+            assert abs(best.value / pw.max() - 1) < 1e-5 and abs(sm.value / pw.sum() - 1) < 1e-5
+
+
 @pytest.mark.parametrize("W", [5456, 8184, 2800])
 def test_pfa_kernel_math_replay_matches_numpy(W):
     """Native W-point prime-factor transforms (csrc/ga_pfa.h) replayed per thread on the CPU: forward transform
