@@ -239,7 +239,8 @@ constexpr int cell_minb(int threads) { return threads <= 128 ? 3 : 2; }
 // multiplies they save); operands of a warp's first pass-A task loaded before the barrier that ends the previous pass C
 // (167 registers): 8.40 -> 8.31 M corr/s.)
 #ifndef GA_PERM_A
-#define GA_PERM_A 1         // bank-conflict-free dealing of the pass-A butterflies (ga_fft3.h passA_slot_to_j)
+#define GA_PERM_A 0         // 1: pass-A butterflies dealt in half-warps that never straddle a padded tile row (no store conflicts, but the
+                            // operand loads fall apart into 128- and 32-byte pieces: measured 14 % SLOWER, round 2) -- off
 #endif
 // SEG: the work item is (chunk, Doppler bin, output segment) -- nseg segments of N2 lags each cover a window of up to
 // N samples; the per-segment records are merged by merge_seg_kernel.  SEG = false is the plain kernel (one segment).
@@ -247,7 +248,7 @@ template <class G, int T, int NW, int GID, bool SEG = false>
 __global__ void __launch_bounds__(T, cell_minb(T)) cell_kernel_tm(const cf *__restrict__ xd, const cf *__restrict__ cext,
                                                        const int *__restrict__ sv_of_block, const cf *__restrict__ tw,
                                                        int n_cells, int n_dop, int dmax, int wlen, CellStat *__restrict__ cells,
-                                                       int nseg = 1, int blk0 = 0)
+                                                       int nseg = 1, int blk0 = 0, int *__restrict__ sched = nullptr)
 {
     static_assert(T % 32 == 0, "tcgen05.ld/st are warp-collective: whole warps only");
     constexpr int NWARP = T / 32;
@@ -269,6 +270,7 @@ __global__ void __launch_bounds__(T, cell_minb(T)) cell_kernel_tm(const cf *__re
     __shared__ float red_best[NWARP], red_sum[NWARP];
     __shared__ int red_idx[NWARP];
     __shared__ uint32_t tm_base_s;
+    __shared__ int next_cell_s;
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
 
     if (wid == 0) {
@@ -283,7 +285,14 @@ __global__ void __launch_bounds__(T, cell_minb(T)) cell_kernel_tm(const cf *__re
     const uint32_t tm_mine = tm_base + ((32u * (uint32_t)(wid & 3)) << 16) + (uint32_t)(wid >> 2) * COL_SLOT;
     const int vw = wid;
 
-    for (int cell = blockIdx.x; cell < n_cells; cell += gridDim.x) {
+    // Cells are handed out in ascending order by a device-wide ticket counter (sched[0]; the first gridDim.x tickets are
+    // the CTA numbers): whichever CTA finishes takes the next cell, so the CTAs of a launch work on a narrow window of
+    // neighbouring (chunk, Doppler bin) cells however long the launch is -- a block spectrum is fetched from HBM once
+    // and shared through L2 by the 73 cells that use it -- and a launch ends with at most one cell of imbalance.
+    // The ticket is drawn by thread 0 at the start of the last sub-sequence (latency hidden) and published through
+    // shared memory at the barrier of the per-cell reduction.  The last CTA to leave rewinds the counter.
+    int next_cell = 0;
+    for (int cell = blockIdx.x; cell < n_cells; cell = next_cell) {
         int item = cell, seg = 0;
         if (SEG) { seg = cell % nseg; item = cell / nseg; }
         const int blk = item / n_dop, dop = item - blk * n_dop - dmax;
@@ -298,6 +307,7 @@ __global__ void __launch_bounds__(T, cell_minb(T)) cell_kernel_tm(const cf *__re
             cell_sub_offsets<G>(s, dop, sp, eoff);
             const cf *xs = xb + (size_t)s * G::N2;
             const cf *cs = cb + (size_t)sp * (2 * G::N2) + eoff;
+            if (s == G::N1 - 1 && tid == 0) next_cell = sched ? (int)gridDim.x + atomicAdd(sched, 1) : cell + (int)gridDim.x;
             for_tasks<ITA>([&](int it) {
                 const int jj = (vw + it * NWARP) * 32 + lane;
                 if (jj < G::NA) cell_passA<G>(GA_PERM_A ? passA_slot_to_j<G>(jj) : jj, s, xs, cs, tw, sm);
@@ -381,7 +391,9 @@ __global__ void __launch_bounds__(T, cell_minb(T)) cell_kernel_tm(const cf *__re
             sum += os;
         }
         if (lane == 0) { red_best[wid] = best; red_idx[wid] = besti; red_sum[wid] = sum; }
+        if (tid == 0) next_cell_s = next_cell;
         __syncthreads();
+        next_cell = next_cell_s;          // rewritten by thread 0 only after the 3*N1 barriers of the next cell
         if (wid == 0) {
             best = lane < NWARP ? red_best[lane] : 0.0f;
             besti = lane < NWARP ? red_idx[lane] : 0x7fffffff;
@@ -403,6 +415,8 @@ __global__ void __launch_bounds__(T, cell_minb(T)) cell_kernel_tm(const cf *__re
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     if (wid == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tm_base), "r"(TM_COLS) : "memory");
+    // every CTA has drawn its last ticket (one past the end) before it gets here: the last one to arrive rewinds
+    if (sched && tid == 0 && atomicAdd(sched + 1, 1) == (int)gridDim.x - 1) { sched[0] = 0; sched[1] = 0; }
 }
 
 // per-segment records [pair][nseg] -> one record per (chunk, Doppler bin): the reference's single scan over i < W

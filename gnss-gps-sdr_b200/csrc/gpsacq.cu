@@ -21,6 +21,7 @@
 #endif
 #define TM_MINB CELL_MINB
 #include "ga_kernels.cuh"
+#include "ga_cell_tma.cuh"
 #include "ga_grid.cuh"
 #include "ga_pfa.cuh"
 #include "ga_frontend.cuh"
@@ -139,6 +140,8 @@ struct gpsacq {
     int sub_blocks, last_launch_blocks; // REF: chunks per kernel launch (a batch is cut into launches whose block spectra stay in L2)
     int nseg;                          // REF: output segments of N2 lags per cell (1 unless W > N2, i.e. FS > 10 MHz)
     CellStat *d_cells_seg;
+    cf *d_chalo; int halo; bool use_tma; CUtensorMap map_x, map_c;    // REF, TMA-staged cell kernel (ga_cell_tma.cuh)
+    int *d_sched;                      // REF: ticket counter of the cell kernel's work queue (ga_kernels.cuh) + exit counter
     int mode, kblocks, wipe_m, block_bytes, cap_acq;
     int q_min, n_q;                    // GRID, native path: replica spectra are stored rotated by -q for q_min <= q < q_min + n_q
     cf *d_crot;
@@ -194,7 +197,7 @@ static int launch_cells_t(gpsacq *h, size_t n_blocks, const int *d_sv, size_t of
     const int grid = std::min(n_cells, h->cell_ctas);
     CellStat *out = SEG ? h->d_cells_seg + off * (size_t)h->ndop * h->nseg : h->d_cells + off * (size_t)h->ndop;
     CellKernel<G, T, NW, GID, SEG>::get()<<<grid, T, h->cell_smem, h->stream>>>(
-        h->d_xd + off * (size_t)h->n, h->d_cext, d_sv, h->d_tw, n_cells, h->ndop, h->dmax, h->w, out, h->nseg, blk0);
+        h->d_xd + off * (size_t)h->n, h->d_cext, d_sv, h->d_tw, n_cells, h->ndop, h->dmax, h->w, out, h->nseg, blk0, h->d_sched);
     CUDA_TRY(h, cudaGetLastError());
     if (SEG) {
         merge_seg_kernel<<<(n_pairs + 255) / 256, 256, 0, h->stream>>>(out, n_pairs, h->nseg, h->d_cells + off * (size_t)h->ndop);
@@ -248,6 +251,74 @@ template <class G, int GID> static int setup_fwd_t(gpsacq *h)
     return 0;
 }
 
+// ---- TMA-staged REF cell kernel (ga_cell_tma.cuh): tensor maps, halo replica layout, launch --------------------------
+#ifndef CELL_TMA_NCW
+#define CELL_TMA_NCW 7          // consumer warps per CTA (+ 1 producer warp), 2 CTAs per SM
+#endif
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                  const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+// 2-D tensor of complex64 elements (8 bytes, described to the TMA as FLOAT64): rows x cols, box = box_cols x box_rows
+static int make_map_2d(gpsacq *h, CUtensorMap *map, void *base, size_t cols, size_t rows, int box_cols, int box_rows)
+{
+    static EncodeTiledFn encode = nullptr;
+    if (!encode) {
+        void *fn = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        CUDA_TRY(h, cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+        if (!fn || qres != cudaDriverEntryPointSuccess) { h->err = "cuTensorMapEncodeTiled is not available in this driver"; return GPSACQ_ECUDA; }
+        encode = (EncodeTiledFn)fn;
+    }
+    const cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows}, strides[1] = {(cuuint64_t)(cols * sizeof(cf))};
+    const cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows}, estr[2] = {1, 1};
+    const CUresult r = encode(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                              CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        char b[128]; snprintf(b, sizeof b, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
+        h->err = b; return GPSACQ_ECUDA;
+    }
+    return 0;
+}
+
+template <class G, int NW, int GID> static int setup_cells_tma_t(gpsacq *h)
+{
+    auto kern = cell_kernel_tma<G, CELL_TMA_NCW, NW, GID>;
+    h->halo = h->dmax / G::N1 + 2;
+    const size_t pitch = (size_t)G::NA + 2 * (size_t)h->halo, rows = (size_t)32 * G::N1 * G::RA;
+    CUDA_TRY(h, cudaMalloc(&h->d_chalo, rows * pitch * sizeof(cf)));
+    int rc = make_map_2d(h, &h->map_x, h->d_xd, G::NA, (size_t)h->cap * G::N1 * G::RA, TMA_BOX_COLS, G::RA);
+    if (!rc) rc = make_map_2d(h, &h->map_c, h->d_chalo, pitch, rows, TMA_BOX_COLS_C, G::RA);
+    if (rc) return rc;
+    h->cell_smem = TmaCellShape<G>::SMEM_BYTES;
+    h->cell_threads = 32 * (CELL_TMA_NCW + 1);
+    h->cell_nw = NW;
+    CUDA_TRY(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, h->cell_smem));
+    CUDA_TRY(h, cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+    h->cell_ctas = 2 * h->sm_count;        // registers (__launch_bounds__), shared memory and TMEM columns are sized for two CTAs per SM
+    h->use_tma = true;
+    return 0;
+}
+
+template <class G> static int build_halo_t(gpsacq *h)
+{
+    replica_halo_kernel<G><<<32 * G::N1 * G::RA, 128, 0, h->stream>>>(h->d_cext, h->halo, h->d_chalo);
+    CUDA_TRY(h, cudaGetLastError());
+    return 0;
+}
+
+template <class G, int NW, int GID>
+static int launch_cells_tma_t(gpsacq *h, size_t n_blocks, const int *d_sv, size_t off, int blk0)
+{
+    const int n_cells = (int)(n_blocks * (size_t)h->ndop);
+    const int grid = std::min(n_cells, h->cell_ctas);
+    cell_kernel_tma<G, CELL_TMA_NCW, NW, GID><<<grid, h->cell_threads, h->cell_smem, h->stream>>>(
+        h->map_x, h->map_c, d_sv, h->d_tw, n_cells, h->ndop, h->dmax, h->w, h->halo, (int)(off * G::N1 * G::RA),
+        h->d_cells + off * (size_t)h->ndop, blk0, h->d_sched, h->d_xd + off * (size_t)h->n);
+    CUDA_TRY(h, cudaGetLastError());
+    return 0;
+}
+
 static int setup_cells(gpsacq *h)
 {
     {
@@ -260,6 +331,10 @@ static int setup_cells(gpsacq *h)
         return h->w <= 7 * G4000::OUT_STRIDE ? setup_cells_t<G4000, CELL_T_4000, 7, GID_4000>(h)
                                              : setup_cells_t<G4000, CELL_T_4000, 10, GID_4000>(h);
     case GID_8000:
+        // the benchmark geometry (W <= 5600): GPSACQ_CELL_TMA=1 selects the kernel whose operands are staged by TMA
+        // (ga_cell_tma.cuh; measured 13 % slower than the __ldg kernel)
+        if (h->w <= 14 * G8000::OUT_STRIDE && h->d_sched && getenv("GPSACQ_CELL_TMA") && atoi(getenv("GPSACQ_CELL_TMA")) > 0)
+            return setup_cells_tma_t<G8000, 14, GID_8000>(h);
         return h->w <= 14 * G8000::OUT_STRIDE ? setup_cells_t<G8000, CELL_T_8000, 14, GID_8000>(h)
                                               : setup_cells_t<G8000, CELL_T_8000_WIDE, 20, GID_8000>(h);
     default:
@@ -271,6 +346,7 @@ static int setup_cells(gpsacq *h)
 
 static int launch_cells(gpsacq *h, size_t n_blocks, const int *d_sv, size_t off, int blk0)
 {
+    if (h->use_tma) return launch_cells_tma_t<G8000, 14, GID_8000>(h, n_blocks, d_sv, off, blk0);
     switch (h->gid) {
     case GID_4000:
         return h->cell_nw == 7 ? launch_cells_t<G4000, CELL_T_4000, 7, GID_4000>(h, n_blocks, d_sv, off, blk0)
@@ -350,7 +426,7 @@ static void free_all(gpsacq *h)
     if (!h) return;
     cudaFree(h->d_tw); cudaFree(h->d_lo); cudaFree(h->d_chip_idx); cudaFree(h->d_blend_a); cudaFree(h->d_blend_b);
     cudaFree(h->d_repl_time); cudaFree(h->d_cext); cudaFree(h->d_xd); cudaFree(h->d_nat); cudaFree(h->d_bits);
-    cudaFree(h->d_crot); cudaFree(h->d_iq_tab); cudaFree(h->d_cells_seg); cudaFree(h->d_sv); cudaFree(h->d_wipe); cudaFree(h->d_xg); cudaFree(h->d_code_w); cudaFree(h->d_cells); cudaFree(h->d_peaks);
+    cudaFree(h->d_crot); cudaFree(h->d_iq_tab); cudaFree(h->d_cells_seg); cudaFree(h->d_sched); cudaFree(h->d_chalo); cudaFree(h->d_sv); cudaFree(h->d_wipe); cudaFree(h->d_xg); cudaFree(h->d_code_w); cudaFree(h->d_cells); cudaFree(h->d_peaks);
     cudaFreeHost(h->h_bits); cudaFreeHost(h->h_sv); cudaFreeHost(h->h_peaks);
     for (int i = 0; i < 4; i++) if (h->ev[i]) cudaEventDestroy(h->ev[i]);
     for (int i = 0; i < 8; i++) if (h->ev_copy[i]) cudaEventDestroy(h->ev_copy[i]);
@@ -429,6 +505,10 @@ static int create_impl(gpsacq *h)
     CUDA_TRY(h, cudaMalloc(&h->d_cells, cap * (size_t)h->ndop * sizeof(CellStat)));
     if (h->nseg > 1) CUDA_TRY(h, cudaMalloc(&h->d_cells_seg, cap * (size_t)h->ndop * h->nseg * sizeof(CellStat)));
     CUDA_TRY(h, cudaMalloc(&h->d_peaks, cap * sizeof(Peak)));
+    if (!getenv("GPSACQ_STATIC_SCHED")) {       // (A/B knob: round-robin cells instead of the ticket queue)
+        CUDA_TRY(h, cudaMalloc(&h->d_sched, 2 * sizeof(int)));
+        CUDA_TRY(h, cudaMemset(h->d_sched, 0, 2 * sizeof(int)));
+    }
     CUDA_TRY(h, cudaMallocHost(&h->h_bits, cap * (size_t)h->chunk_bytes));
     CUDA_TRY(h, cudaMallocHost(&h->h_sv, cap * sizeof(int)));
     CUDA_TRY(h, cudaMallocHost(&h->h_peaks, cap * sizeof(Peak)));
@@ -462,6 +542,7 @@ static int create_impl(gpsacq *h)
     CUDA_TRY(h, cudaGetLastError());
     rc = launch_fwd(h, 1, 32, nullptr, h->d_cext);
     if (rc) return rc;
+    if (h->use_tma) { rc = build_halo_t<G8000>(h); if (rc) return rc; }
     CUDA_TRY(h, cudaStreamSynchronize(h->stream));
     return 0;
 }
