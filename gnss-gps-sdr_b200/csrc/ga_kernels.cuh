@@ -226,7 +226,7 @@ template <int IT, class F> __device__ __forceinline__ void for_tasks(F &&f)
 }
 // CTAs per SM a cell-kernel shape is sized for: 128-thread CTAs run three per SM (201 KB of shared memory, 136
 // registers), the 256/448-thread shapes two
-constexpr int cell_minb(int threads) { return threads <= 128 ? 3 : 2; }
+constexpr int cell_minb(int threads) { return threads <= 160 ? 3 : 2; }
 
 // (400 butterflies per pass are 13 warp-tasks, so one of a CTA's four warps runs 4 tasks per pass and the others 3.
 // Warps sit on sub-partition (hardware warp slot mod 4); the hardware hands co-resident CTAs staggered warp slots
@@ -260,21 +260,28 @@ __global__ void __launch_bounds__(T, cell_minb(T)) cell_kernel_tm(const cf *__re
     constexpr bool SPLIT_C = T <= 256;                             // see pass C: only where 128 registers are available (2 x 256 threads)
     constexpr uint32_t COLS_THREAD = ITC * 2 * NW;                 // accumulator floats per thread
     constexpr uint32_t COL_SLOT = (COLS_THREAD + 7u) & ~7u;        // column range of one warp "row" (4 warps share the lanes)
-    constexpr uint32_t TM_COLS = pow2_at_least(COL_SLOT * cdiv(NWARP, 4));
+    // Five warps (160 threads): the fifth warp shares the TMEM lanes of warp 0 and would need a second column slot -- 176
+    // columns, 256 allocated, too many for three CTAs per SM.  It runs at most ITC - 1 tasks per pass, though: its first
+    // task's accumulators go into the free tail of the 128-column allocation and the second into a separate 32-column
+    // allocation (160 columns per CTA, 480 per SM).
+    constexpr bool FIVE = NWARP == 5 && ITC == 3 && NTC <= 4 + 2 * NWARP && COL_SLOT + 2 * NW <= 128 && 2 * NW <= 32;
+    constexpr uint32_t TM_COLS = FIVE ? 128u : pow2_at_least(COL_SLOT * cdiv(NWARP, 4));
+    constexpr uint32_t TM_COLS_ALL = FIVE ? 160u : TM_COLS;
 #ifndef GA_NO_TM_ASSERT
-    static_assert(TM_COLS * cell_minb(T) <= 512 || G::SMEM_ELEMS * sizeof(cf) * cell_minb(T) > 227 * 1024,
+    static_assert(TM_COLS_ALL * cell_minb(T) <= 512 || G::SMEM_ELEMS * sizeof(cf) * cell_minb(T) > 227 * 1024,
                   "cell_minb(T) CTAs per SM must fit in the 512 TMEM columns");
 #endif
     extern __shared__ __align__(16) unsigned char smem_raw[];
     cf *sm = reinterpret_cast<cf *>(smem_raw);
     __shared__ float red_best[NWARP], red_sum[NWARP];
     __shared__ int red_idx[NWARP];
-    __shared__ uint32_t tm_base_s;
+    __shared__ uint32_t tm_base_s, tm_base2_s;
     __shared__ int next_cell_s;
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
 
     if (wid == 0) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tm_base_s)), "r"(TM_COLS) : "memory");
+        if (FIVE) asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tm_base2_s)), "r"(32u) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -283,6 +290,7 @@ __global__ void __launch_bounds__(T, cell_minb(T)) cell_kernel_tm(const cf *__re
     const uint32_t tm_base = tm_base_s;
     // this warp's private window: lanes 32*(wid%4).., columns (wid/4)*COL_SLOT..
     const uint32_t tm_mine = tm_base + ((32u * (uint32_t)(wid & 3)) << 16) + (uint32_t)(wid >> 2) * COL_SLOT;
+    const uint32_t tm_second = FIVE ? tm_base2_s : 0u;      // fifth warp, second task (lanes 0..31 of the 32-column allocation)
     const int vw = wid;
 
     // Cells are handed out in ascending order by a device-wide ticket counter (sched[0]; the first gridDim.x tickets are
@@ -329,7 +337,7 @@ __global__ void __launch_bounds__(T, cell_minb(T)) cell_kernel_tm(const cf *__re
                     const int jc = act ? j : G::NC - 1;
                     cf p[G::RC];
                     const int tau0 = passC<G, +1>(jc, sm, p);
-                    const uint32_t col = tm_mine + (uint32_t)(it * 2 * NW);
+                    const uint32_t col = (FIVE && wid == 4 && it == 1) ? tm_second : tm_mine + (uint32_t)(it * 2 * NW);
                     // acc = TMEM accumulators + p * ktab[s]
                     auto accumulate = [&](float (&a)[2 * NW]) {
                         if (s == 0) {
@@ -414,7 +422,10 @@ __global__ void __launch_bounds__(T, cell_minb(T)) cell_kernel_tm(const cf *__re
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
-    if (wid == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tm_base), "r"(TM_COLS) : "memory");
+    if (wid == 0) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tm_base), "r"(TM_COLS) : "memory");
+        if (FIVE) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tm_second), "r"(32u) : "memory");
+    }
     // every CTA has drawn its last ticket (one past the end) before it gets here: the last one to arrive rewinds
     if (sched && tid == 0 && atomicAdd(sched + 1, 1) == (int)gridDim.x - 1) { sched[0] = 0; sched[1] = 0; }
 }

@@ -91,7 +91,7 @@ __device__ __noinline__ void pfa_passC_exact(int jc, const cf *sm, int t0, float
 template <class G, int T, int MINB, bool MULTI>
 __global__ void __launch_bounds__(T, MINB) pfa_cell_kernel(const cf *__restrict__ xg, const cf *__restrict__ crep,
                                                            int n_cells, int n_dop, int dmax, int n_base, int q_min, int kblocks,
-                                                           CellStat *__restrict__ cells)
+                                                           CellStat *__restrict__ cells, int *__restrict__ sched = nullptr)
 {
     static_assert(T % 32 == 0, "whole warps only");
     constexpr int NWARP = T / 32;
@@ -107,6 +107,7 @@ __global__ void __launch_bounds__(T, MINB) pfa_cell_kernel(const cf *__restrict_
     __shared__ float red_best[NWARP], red_sum[NWARP];
     __shared__ int red_idx[NWARP];
     __shared__ uint32_t tm_base_s;
+    __shared__ int next_cell_s;
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
 
     uint32_t tm_base = 0, tm_mine = 0;
@@ -122,7 +123,10 @@ __global__ void __launch_bounds__(T, MINB) pfa_cell_kernel(const cf *__restrict_
         tm_mine = tm_base + ((32u * (uint32_t)(wid & 3)) << 16) + (uint32_t)(wid >> 2) * COL_SLOT;
     }
 
-    for (int cell = blockIdx.x; cell < n_cells; cell += gridDim.x) {
+    // cells in ascending order from a device-wide ticket counter, as in cell_kernel_tm (ga_kernels.cuh): the 32 PRN cells
+    // that share a block spectrum run at the same time on neighbouring CTAs, and a launch ends with one cell of imbalance
+    int next_cell = 0;
+    for (int cell = blockIdx.x; cell < n_cells; cell = next_cell) {
         const int acq = cell / (n_dop * 32), r = cell - acq * (n_dop * 32);
         const int di = r >> 5, prn = r & 31;
         const cf *cs = crep + (size_t)prn * G::W;
@@ -142,6 +146,7 @@ __global__ void __launch_bounds__(T, MINB) pfa_cell_kernel(const cf *__restrict_
 
         for (int k = 0; k < kblocks; k++) {
             const cf *xs = xg + ((size_t)(acq * kblocks + k) * xstride + xsel) * G::W;
+            if (k == kblocks - 1 && tid == 0) next_cell = sched ? (int)gridDim.x + atomicAdd(sched, 1) : cell + (int)gridDim.x;
             if (PIPE_A && ITA > 1) {
                 // software-pipelined pass A: the operand rows of the warp's NEXT task are in flight (registers)
                 // while the current task multiplies and runs its butterfly -- one exposed L2 round trip per
@@ -231,10 +236,12 @@ __global__ void __launch_bounds__(T, MINB) pfa_cell_kernel(const cf *__restrict_
                     sum += os;
                 }
                 if (lane == 0) { red_best[wid] = best; red_idx[wid] = besti; red_sum[wid] = sum; }
+                if (tid == 0) next_cell_s = next_cell;
             }
             if (MULTI) asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
             __syncthreads();                                        // smem is rewritten by the next pass A
         }
+        next_cell = next_cell_s;        // thread 0 rewrites it only after two more block barriers
         if (wid == 0) {
             // warp 0 finishes the record while the other warps start the next cell (they touch red_* again
             // only after the next cell's barriers, which warp 0 takes part in)
@@ -261,6 +268,7 @@ __global__ void __launch_bounds__(T, MINB) pfa_cell_kernel(const cf *__restrict_
         __syncthreads();
         if (wid == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tm_base), "r"(TM_COLS) : "memory");
     }
+    if (sched && tid == 0 && atomicAdd(sched + 1, 1) == (int)gridDim.x - 1) { sched[0] = 0; sched[1] = 0; }     // last CTA out rewinds
 }
 
 }  // namespace ga

@@ -101,8 +101,10 @@ enum { XID_10000 = 7, XID_8000 = 8, XID_4000 = 9, XID_4096 = 10, XID_2048 = 11 }
 #define CELL_T_4000 128     // 3 CTAs/SM like the benchmark geometry (+3 % over 256 x 2)
 #endif
 #ifndef CELL_T_8000
-#define CELL_T_8000 128     // 4 warps (one per SM sub-partition) x 3 CTAs/SM, 13 tasks per pass dealt over the warps, 136 registers;
-                            // 448 threads x 2 CTAs (one task per warp, 72 registers) measures 1.7 % slower
+#define CELL_T_8000 160     // 5 warps x 3 CTAs/SM: the 13 tasks of a pass are dealt 3/3/3/2/2 (three rounds; four warps need four),
+                            // 118 registers, the fifth warp's accumulators in a second small TMEM allocation (ga_kernels.cuh).
+                            // Round 2, ticket scheduler, one B200: 160 x 3 9.00 M corr/s, 128 x 3 8.91, 256 x 2 8.91, 224 x 2 8.67,
+                            // 448 x 2 8.53, 192 x 2 8.14
 #endif
 #define CELL_T_8000_WIDE 448  // search windows above 5600 samples (20 accumulators per butterfly): too many TMEM columns for 3 CTAs/SM
 #ifndef CELL_T_10000
@@ -475,9 +477,12 @@ static int create_impl(gpsacq *h)
     h->chunk_samples = ((h->n + 4095) / 4096) * 4096;         // whole 512-byte packets (:129,:135-141)
     h->chunk_bytes = h->chunk_samples / 8;
     h->cap = c.max_blocks > 0 ? c.max_blocks : 512;
-    {   // chunks per launch: 128 x 320 KB = 41 MB of block spectra + 20 MB of replica spectra stay L2-resident
+    {   // chunks per launch.  With the ticket scheduler of the cell kernel (ga_kernels.cuh) the CTAs of a launch work on a
+        // narrow window of neighbouring cells whatever its length, so a whole batch goes out as ONE launch triple
+        // (measured: 8.90 M corr/s, against 8.74 M cut into 128-chunk launches).  Round-robin cells (GPSACQ_STATIC_SCHED)
+        // drift apart in long launches and want 128-chunk launches whose block spectra stay in L2.
         const char *e = getenv("GPSACQ_SUB_BLOCKS");
-        h->sub_blocks = (e && atoi(e) > 0) ? atoi(e) : 128;
+        h->sub_blocks = (e && atoi(e) > 0) ? atoi(e) : (getenv("GPSACQ_STATIC_SCHED") ? 128 : h->cap);
     }
     if (h->w <= G4000::N2) { h->gid = GID_4000; h->n1 = G4000::N1; h->n2 = G4000::N2; }
     else if (h->w <= G8000::N2) { h->gid = GID_8000; h->n1 = G8000::N1; h->n2 = G8000::N2; }
@@ -628,7 +633,7 @@ template <class G, int T, int MINB, bool MULTI> struct PfaOps {
         const int n_cells = (int)(n_acq * 32 * (size_t)h->ndop);
         const int grid = std::min(n_cells, h->cell_ctas);
         pfa_cell_kernel<G, T, MINB, MULTI><<<grid, T, h->cell_smem, h->stream>>>(h->d_xg, h->d_crot ? h->d_crot : h->d_cext, n_cells, h->ndop,
-                                                                                 h->dmax, h->n_base, h->q_min, h->kblocks, h->d_cells);
+                                                                                 h->dmax, h->n_base, h->q_min, h->kblocks, h->d_cells, h->d_sched);
         CUDA_TRY(h, cudaGetLastError());
         return 0;
     }
@@ -753,6 +758,10 @@ static int create_grid(gpsacq *h)
     CUDA_TRY(h, cudaMalloc(&h->d_nat, L * sizeof(cf)));
     CUDA_TRY(h, cudaMalloc(&h->d_bits, cap * (size_t)h->chunk_bytes));
     CUDA_TRY(h, cudaMalloc(&h->d_cells, cap * 32 * (size_t)h->ndop * sizeof(CellStat)));
+    if (!getenv("GPSACQ_STATIC_SCHED")) {       // ticket counter of pfa_cell_kernel's work queue (A/B knob as in REF mode)
+        CUDA_TRY(h, cudaMalloc(&h->d_sched, 2 * sizeof(int)));
+        CUDA_TRY(h, cudaMemset(h->d_sched, 0, 2 * sizeof(int)));
+    }
     CUDA_TRY(h, cudaMalloc(&h->d_peaks, cap * 32 * sizeof(Peak)));
     CUDA_TRY(h, cudaMallocHost(&h->h_bits, cap * (size_t)h->chunk_bytes));
     CUDA_TRY(h, cudaMallocHost(&h->h_peaks, cap * 32 * sizeof(Peak)));

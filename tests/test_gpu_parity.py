@@ -322,6 +322,48 @@ def test_full_batch_properties(engines, siggen):
     assert np.allclose(neg["snr"], got["snr"][:64], rtol=1e-5)
 
 
+# ---- the cell kernel's variants: work queue vs round robin, operands by __ldg vs staged by TMA -----------------
+def test_ticket_scheduler_matches_round_robin(ga, monkeypatch):
+    """Cells drawn from the device-wide ticket counter (default) or dealt round robin (GPSACQ_STATIC_SCHED=1) are the
+    same cells: byte-identical records, over several back-to-back launches (the counter rewinds itself)."""
+    c = CAPTURES["nottingham"]
+    data = c["bin"].read_bytes()
+    with ga.Acquisition(c["fc"], c["fs"], max_blocks=128) as acq:
+        a = [acq.search_blocks(data).copy() for _ in range(3)]
+    monkeypatch.setenv("GPSACQ_STATIC_SCHED", "1")
+    with ga.Acquisition(c["fc"], c["fs"], max_blocks=128) as acq:
+        b = acq.search_blocks(data).copy()
+    for x in a:
+        assert x.tobytes() == b.tobytes()
+
+
+def test_tma_staged_kernel_matches_ldg_kernel(ga, monkeypatch):
+    """GPSACQ_CELL_TMA=1 (ga_cell_tma.cuh: cp.async.bulk.tensor + mbarrier ring, replica spectra in the halo layout)
+    against the default kernel on the Nottingham fixture and on ragged batch sizes: same integers, per-cell powers
+    within 2e-6 (only the summation order of a thread's power sums differs), and the reference's golden returns."""
+    c = CAPTURES["nottingham"]
+    data = c["bin"].read_bytes()
+    with ga.Acquisition(c["fc"], c["fs"], max_blocks=128) as acq:
+        ref = acq.search_blocks(data).copy()
+        ref_cells = acq.cell_stats(5).copy()
+    monkeypatch.setenv("GPSACQ_CELL_TMA", "1")
+    with ga.Acquisition(c["fc"], c["fs"], max_blocks=128) as acq:
+        assert acq.info["cell_threads"] == 256                     # 7 consumer warps + the producer warp
+        got = acq.search_blocks(data).copy()
+        cells = acq.cell_stats(5).copy()
+        small = [acq.search_blocks(data[: n * 5120]).copy() for n in (1, 3, 37)]
+    same = (got["lo_shift"] == ref["lo_shift"]) & (got["ca_shift"] == ref["ca_shift"])
+    assert same[ref["snr"] >= 20].all() and same.mean() > 0.98       # (a noise-only chunk may flip between two bins whose snr ties to 1e-7)
+    assert np.array_equal(got["sv"], ref["sv"]) and np.array_equal(got["flags"], ref["flags"])
+    assert np.allclose(got["snr"], ref["snr"], rtol=2e-6) and np.allclose(got["max_pwr"][same], ref["max_pwr"][same], rtol=2e-6)
+    assert np.array_equal(cells["max_idx"], ref_cells["max_idx"])
+    assert np.allclose(cells["tot_pwr"], ref_cells["tot_pwr"], rtol=2e-6)
+    for n, s_ in zip((1, 3, 37), small):
+        assert s_.tobytes() == got[:n].tobytes()
+    gold = np.load(c["peaks"])
+    compare_peaks(got, gold)
+
+
 # ---- device-pointer API on torch's stream ---------------------------------------------------------------
 def test_device_api_on_torch_stream(ga, engines):
     import torch
