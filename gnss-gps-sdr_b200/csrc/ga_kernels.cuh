@@ -92,6 +92,19 @@ struct RealSrc {      // SearchInit(): real replica, imaginary part 0 (:101-102)
 // its RC outputs back into the row it has just read (nobody else touches that row), and after a barrier the CTA
 // streams the N2 values out in natural order with coalesced float2 stores (the read side walks shared memory with
 // the odd stride Q: conflict-free).
+//
+// MODE 0, pass A input by table (lomask != nullptr).  The radix-N1 gather of Sample() -- z = x[n2] + sum_n1 x[N2*n1 + n2] *
+// K1[s][n1] with x = (+-1, +-1) from one data bit XOR the two LO bits (c/search_offline.cpp:143-153) -- has only 4^N1
+// possible values per sub-sequence s: the CTA builds them once in shared memory (same operation order as fwd_passA, so
+// the same bits) and a sample group costs N1 byte loads, a few shifts and ONE table load instead of N1 unpack/select/
+// multiply-add chains.  The LO bits of the N1 samples of a group come packed from lomask[n2] (2 bits per sample), the
+// data bit is spread over both and XORed in.  N1 = 10 uses two groups of five (1024-entry tables).
+template <class G> struct FwdLut {
+    static constexpr int GS = G::N1 <= 5 ? G::N1 : 5, NG = (G::N1 + GS - 1) / GS;
+    static constexpr int ENTRIES = 1 << (2 * GS);
+    static constexpr int BYTES = NG * ENTRIES * (int)sizeof(cf);
+    static_assert(G::N2 % 8 == 0, "sample groups must sit at the same bit of their bytes");
+};
 #ifndef FWD_MINB
 #define FWD_MINB 2     // measured: 2 CTAs/SM at 126 registers beat 3 at 80 (spills)
 #endif
@@ -99,14 +112,44 @@ template <class G, int T, int MODE, int GID>
 __global__ void __launch_bounds__(T, MODE == 0 ? FWD_MINB : 1) fwd_kernel(const unsigned char *__restrict__ bits, int chunk_bytes,
                                                 const unsigned char *__restrict__ lo,
                                                 const float *__restrict__ repl_time,
-                                                const cf *__restrict__ tw, cf *__restrict__ out)
+                                                const cf *__restrict__ tw, cf *__restrict__ out,
+                                                const unsigned int *__restrict__ lomask = nullptr)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     cf *sm = reinterpret_cast<cf *>(smem_raw);
     const int item = blockIdx.x / G::N1, s = blockIdx.x - item * G::N1;
     const cf *k1s = c_k1tab[GID] + s * G::N1;
 
-    if (MODE == 0) {
+    if (MODE == 0 && lomask != nullptr) {
+        typedef FwdLut<G> L;
+        cf *lut = sm + G::SMEM_ELEMS;
+        for (int e = threadIdx.x; e < L::NG * L::ENTRIES; e += T) {
+            const int g = e / L::ENTRIES, code = e - g * L::ENTRIES, first = g * L::GS;
+            const int last = first + L::GS < G::N1 ? first + L::GS : G::N1;
+            auto x = [&](int n1) { const int c = (code >> (2 * (n1 - first))) & 3; return mk((c & 1) ? -1.0f : 1.0f, (c & 2) ? -1.0f : 1.0f); };
+            cf z = first == 0 ? x(0) : cmul(x(first), k1s[first]);
+            for (int n1 = first + 1; n1 < last; n1++) cfma(z, x(n1), k1s[n1]);
+            lut[e] = z;
+        }
+        __syncthreads();
+        const unsigned char *chunk = bits + (size_t)item * chunk_bytes;
+        for (int j = threadIdx.x; j < G::NA; j += T) {
+            cf p[G::RA];
+#pragma unroll
+            for (int a = 0; a < G::RA; a++) {
+                const int n2 = a * G::NA + j, sh = n2 & 7;
+                const unsigned char *b = chunk + (n2 >> 3);
+                unsigned idx = 0;
+#pragma unroll
+                for (int n1 = 0; n1 < G::N1; n1++) idx |= (((unsigned)b[n1 * (G::N2 / 8)] >> sh) & 1u) * 3u << (2 * n1);
+                idx ^= lomask[n2];
+                cf z = lut[idx & (L::ENTRIES - 1)];
+                if (L::NG > 1) z = cadd(z, lut[L::ENTRIES + (idx >> (2 * L::GS))]);
+                p[a] = (s == 0) ? z : cmul(z, tw_load<-1>(tw, n2 * s));
+            }
+            passA_finish<G, -1>(p, j, 0, tw, sm);
+        }
+    } else if (MODE == 0) {
         BitSrc src{bits + (size_t)item * chunk_bytes, lo};
         for (int j = threadIdx.x; j < G::NA; j += T) fwd_passA<G>(j, s, src, k1s, tw, sm);
     } else {

@@ -159,6 +159,7 @@ struct gpsacq {
     // device
     cf *d_tw;
     unsigned char *d_lo;
+    unsigned int *d_lomask;            // REF forward kernel: LO bits of the N1 samples of a radix-N1 group, 2 bits each (ga_kernels.cuh)
     unsigned short *d_chip_idx;
     float *d_blend_a, *d_blend_b, *d_repl_time;
     cf *d_cext, *d_xd, *d_nat;
@@ -238,9 +239,10 @@ template <class G, int MODE, int GID>
 static int launch_fwd_t(gpsacq *h, size_t n_items, const unsigned char *d_bits, cf *out)
 {
     auto kern = fwd_kernel<G, FWD_T, MODE, GID>;
-    const int smem = (int)(G::SMEM_ELEMS * sizeof(cf));       // opted in once by setup_fwd_t()
+    // opted in once by setup_fwd_t(); MODE 0 carries the sample-group tables behind the tile
+    const int smem = (int)(G::SMEM_ELEMS * sizeof(cf)) + (MODE == 0 && h->d_lomask ? FwdLut<G>::BYTES : 0);
     kern<<<(unsigned)(n_items * G::N1), FWD_T, smem, h->stream>>>(d_bits, h->chunk_bytes, h->d_lo, h->d_repl_time,
-                                                                  h->d_tw, out);
+                                                                  h->d_tw, out, MODE == 0 ? h->d_lomask : nullptr);
     CUDA_TRY(h, cudaGetLastError());
     return 0;
 }
@@ -248,7 +250,7 @@ static int launch_fwd_t(gpsacq *h, size_t n_items, const unsigned char *d_bits, 
 template <class G, int GID> static int setup_fwd_t(gpsacq *h)
 {
     const int smem = (int)(G::SMEM_ELEMS * sizeof(cf));
-    CUDA_TRY(h, cudaFuncSetAttribute(fwd_kernel<G, FWD_T, 0, GID>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    CUDA_TRY(h, cudaFuncSetAttribute(fwd_kernel<G, FWD_T, 0, GID>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem + FwdLut<G>::BYTES));
     CUDA_TRY(h, cudaFuncSetAttribute(fwd_kernel<G, FWD_T, 1, GID>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     return 0;
 }
@@ -426,7 +428,7 @@ static void build_lo_table(double fc, double fs, int n, std::vector<unsigned cha
 static void free_all(gpsacq *h)
 {
     if (!h) return;
-    cudaFree(h->d_tw); cudaFree(h->d_lo); cudaFree(h->d_chip_idx); cudaFree(h->d_blend_a); cudaFree(h->d_blend_b);
+    cudaFree(h->d_tw); cudaFree(h->d_lo); cudaFree(h->d_lomask); cudaFree(h->d_chip_idx); cudaFree(h->d_blend_a); cudaFree(h->d_blend_b);
     cudaFree(h->d_repl_time); cudaFree(h->d_cext); cudaFree(h->d_xd); cudaFree(h->d_nat); cudaFree(h->d_bits);
     cudaFree(h->d_crot); cudaFree(h->d_iq_tab); cudaFree(h->d_cells_seg); cudaFree(h->d_sched); cudaFree(h->d_chalo); cudaFree(h->d_sv); cudaFree(h->d_wipe); cudaFree(h->d_xg); cudaFree(h->d_code_w); cudaFree(h->d_cells); cudaFree(h->d_peaks);
     cudaFreeHost(h->h_bits); cudaFreeHost(h->h_sv); cudaFreeHost(h->h_peaks);
@@ -531,6 +533,13 @@ static int create_impl(gpsacq *h)
     std::vector<unsigned char> lo;
     build_lo_table(c.fc, c.fs, h->chunk_samples, lo);
     CUDA_TRY(h, cudaMemcpy(h->d_lo, lo.data(), lo.size(), cudaMemcpyHostToDevice));
+    if (!getenv("GPSACQ_FWD_NOLUT")) {      // (A/B knob: per-sample unpack + multiply-add instead of the group tables)
+        std::vector<unsigned int> lm((size_t)h->n2, 0u);
+        for (int n2 = 0; n2 < h->n2; n2++)
+            for (int n1 = 0; n1 < h->n1; n1++) lm[n2] |= (unsigned)(lo[(size_t)h->n2 * n1 + n2] & 3) << (2 * n1);
+        CUDA_TRY(h, cudaMalloc(&h->d_lomask, lm.size() * sizeof(unsigned int)));
+        CUDA_TRY(h, cudaMemcpy(h->d_lomask, lm.data(), lm.size() * sizeof(unsigned int), cudaMemcpyHostToDevice));
+    }
     std::vector<unsigned short> ci; std::vector<float> ba, bb;
     build_code_nco(c.fs_replica > 0 ? c.fs_replica : c.fs, h->n, ci, ba, bb);     // SearchInit()-time FS (:76)
     CUDA_TRY(h, cudaMemcpy(h->d_chip_idx, ci.data(), n * sizeof(unsigned short), cudaMemcpyHostToDevice));
@@ -963,15 +972,28 @@ int gpsacq_search_blocks(gpsacq_t *h, const uint8_t *bits, size_t n_blocks, cons
             if (sv < 0 || sv >= GPSACQ_NUM_SATS) { h->err = "sv_of_block entry out of range 0..31"; return GPSACQ_EINVAL; }
             h->h_sv[b] = sv;
         }
-        const size_t n_slices = nb >= 256 ? 4 : nb >= 64 ? 2 : 1;
+        // Slices: 1/8, 1/8, 1/4, 1/2 of the batch -- the first one small, so that the GPU starts early and only its
+        // staging + transfer is exposed.  A caller buffer that is page-locked already (cudaHostAlloc / cudaHostRegister /
+        // torch pin_memory) is handed to the copy engine as it is; pageable memory goes through the pinned staging buffer.
+        size_t cut[5] = {0, nb / 8, nb / 4, nb / 2, nb};
+        size_t n_slices = 4;
+        if (nb < 256) { n_slices = nb >= 64 ? 2 : 1; cut[1] = n_slices == 2 ? nb / 2 : nb; cut[2] = nb; }
+        bool pinned = false;
+        {
+            cudaPointerAttributes attr;
+            if (cudaPointerGetAttributes(&attr, bits + done * cb) == cudaSuccess) pinned = attr.type == cudaMemoryTypeHost;
+            else cudaGetLastError();          // (plain malloc memory makes older runtimes return an error: not pinned)
+        }
         // the previous batch's kernels may still read d_bits / d_sv: the copy stream waits for them
         CUDA_TRY(h, cudaEventRecord(h->ev_done, h->stream));
         CUDA_TRY(h, cudaStreamWaitEvent(h->copy_stream, h->ev_done, 0));
         CUDA_TRY(h, cudaMemcpyAsync(h->d_sv, h->h_sv, nb * sizeof(int), cudaMemcpyHostToDevice, h->copy_stream));
         for (size_t i = 0; i < n_slices; i++) {
-            const size_t lo = nb * i / n_slices, n = nb * (i + 1) / n_slices - lo;
-            memcpy(h->h_bits + lo * cb, bits + (done + lo) * cb, n * cb);
-            CUDA_TRY(h, cudaMemcpyAsync(h->d_bits + lo * cb, h->h_bits + lo * cb, n * cb, cudaMemcpyHostToDevice, h->copy_stream));
+            const size_t lo = cut[i], n = cut[i + 1] - lo;
+            if (n == 0) continue;
+            const unsigned char *src = bits + (done + lo) * cb;
+            if (!pinned) { memcpy(h->h_bits + lo * cb, src, n * cb); src = h->h_bits + lo * cb; }
+            CUDA_TRY(h, cudaMemcpyAsync(h->d_bits + lo * cb, src, n * cb, cudaMemcpyHostToDevice, h->copy_stream));
             CUDA_TRY(h, cudaEventRecord(h->ev_copy[i], h->copy_stream));
             CUDA_TRY(h, cudaStreamWaitEvent(h->stream, h->ev_copy[i], 0));
             const int rc = search_device_impl(h, h->d_bits + lo * cb, n, h->d_sv + lo, (gpsacq_peak *)(h->d_peaks + lo), lo, i + 1 == n_slices);

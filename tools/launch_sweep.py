@@ -36,8 +36,8 @@ for sub in subs:
     torch.cuda.synchronize(dev)
     ms = e0.elapsed_time(e1) / reps
     pk = np.frombuffer(d_out.cpu().numpy().tobytes(), ga.PEAK_DTYPE)
-    print("%s %s sub=%d: %.3f ms per %d chunks -> %.3f Mcorr/s (contract frac %.3f)  last launch cells %.3f ms  checksum %.6e" % (
+    print("%s %s sub=%d: %.3f ms per %d chunks -> %.3f Mcorr/s (contract frac %.3f)  last launch cells %.3f ms fwd %.3f ms  checksum %.6e" % (
         os.environ.get("GPSACQ_LIB", "default"), "static" if os.environ.get("GPSACQ_STATIC_SCHED") else "ticket", sub, ms, nb,
-        nb * acq.n_doppler / ms / 1e3, nb * acq.n_doppler / ms * 1e3 * 640016 / 6550.1e9, acq.stage_times()["cells_ms"],
+        nb * acq.n_doppler / ms / 1e3, nb * acq.n_doppler / ms * 1e3 * 640016 / 6550.1e9, acq.stage_times()["cells_ms"], acq.stage_times()["fwd_ms"],
         float(pk["snr"].astype(np.float64).sum())), flush=True)
     acq.close()
