@@ -74,13 +74,18 @@ __global__ void pfa_rotate_replicas_kernel(const cf *__restrict__ crep, int q_mi
 
 // slow path of the K = 1 statistics: redo one pass-C butterfly (its inputs are still in shared memory)
 // comparing lags on every tie.  Kept out of line: it is practically never executed.
+// (running statistics go in and come back BY VALUE: reference parameters of a non-inlined function put best/besti/sum
+// into a stack frame that every butterfly then stored to -- the "local memory" traffic ncu showed in round 1)
+struct PfaAcc { float best; int besti; float sum; };
 template <class G>
-__device__ __noinline__ void pfa_passC_exact(int jc, const cf *sm, int t0, float &best, int &besti, float &sum)
+__device__ __noinline__ PfaAcc pfa_passC_exact(int jc, const cf *sm, int t0, float best, int besti, float sum)
 {
     PfaPeakExact<G> pk;
     pk.init(t0);
     pfa_passC<G, +1>(jc, sm, [&](auto wc, cf v) { pk.template put<decltype(wc)::value>(fmaf(v.x, v.x, v.y * v.y)); });
     pk.merge(best, besti, sum);
+    PfaAcc r; r.best = best; r.besti = besti; r.sum = sum;
+    return r;
 }
 
 // The native GRID cell kernel.  cell = (acquisition, Doppler bin, PRN), PRN fastest (the 32 cells that
@@ -193,7 +198,7 @@ __global__ void __launch_bounds__(T, MINB) pfa_cell_kernel(const cf *__restrict_
                         pfa_passC<G, +1>(jc, sm, [&](auto wc, cf v) { pk.template put<decltype(wc)::value>(fmaf(v.x, v.x, v.y * v.y)); });
                         if (act) {
                             if (!pk.tie) pk.merge(best, besti, sum);
-                            else pfa_passC_exact<G>(jc, sm, t0, best, besti, sum);
+                            else { const PfaAcc r = pfa_passC_exact<G>(jc, sm, t0, best, besti, sum); best = r.best; besti = r.besti; sum = r.sum; }
                         }
                     } else {
                         float pw[NWP];
