@@ -209,4 +209,45 @@ GA_HD void fwd_passA(int j, int s, const Src &src, const cf *k1s, const cf *tw, 
     passA_finish<G, -1>(p, j, 0, tw, sm);
 }
 
+// ---- the same pass-A input by table ---------------------------------------------------------------
+// In Sample() (c/search_offline.cpp:143-153) a time sample is (+-1, +-1): one data bit XOR the LO's cos / sin bit.  The
+// radix-N1 gather z = x[n2] + sum_{n1>=1} x[N2*n1 + n2] * K1[s][n1] of fwd_passA therefore takes one of 4^N1 values per
+// sub-sequence s.  FwdLut<G>: the values of groups of GS <= 5 samples (N1 = 10: two groups, z = z_0 + z_1), built in
+// the operation order of fwd_passA -- for N1 <= 5 the table value IS what fwd_passA computes, bit for bit.
+// Index: 2 bits per sample, bit 0 = "real part negative" = data ^ lo_cos, bit 1 = "imaginary part negative" = data ^ lo_sin.
+template <class G> struct FwdLut {
+    static constexpr int GS = G::N1 <= 5 ? G::N1 : 5, NG = (G::N1 + GS - 1) / GS;
+    static constexpr int ENTRIES = 1 << (2 * GS);
+    static constexpr int BYTES = NG * ENTRIES * (int)sizeof(cf);
+    static_assert(G::N2 % 8 == 0, "the samples of a group must sit at the same bit of their bytes");
+};
+template <class G> GA_HD cf fwd_lut_entry(int e, const cf *k1s)
+{
+    typedef FwdLut<G> L;
+    const int g = e / L::ENTRIES, code = e - g * L::ENTRIES, first = g * L::GS;
+    const int last = first + L::GS < G::N1 ? first + L::GS : G::N1;
+    const int c0 = code & 3;
+    const cf x0 = mk((c0 & 1) ? -1.0f : 1.0f, (c0 & 2) ? -1.0f : 1.0f);
+    cf z = first == 0 ? x0 : cmul(x0, k1s[first]);
+    for (int n1 = first + 1; n1 < last; n1++) {
+        const int c = (code >> (2 * (n1 - first))) & 3;
+        cfma(z, mk((c & 1) ? -1.0f : 1.0f, (c & 2) ? -1.0f : 1.0f), k1s[n1]);
+    }
+    return z;
+}
+// lomask_n2 = sum_n1 (lo[N2*n1 + n2] & 3) << 2*n1, lo[n] = lo_cos bit | lo_sin bit << 1 at sample n
+template <class G> GA_HD cf fwd_lut_gather(const unsigned char *chunk, int n2, unsigned lomask_n2, const cf *lut)
+{
+    typedef FwdLut<G> L;
+    const int sh = n2 & 7;
+    const unsigned char *b = chunk + (n2 >> 3);
+    unsigned idx = 0;
+    GA_UNROLL
+    for (int n1 = 0; n1 < G::N1; n1++) idx |= ((((unsigned)b[n1 * (G::N2 / 8)] >> sh) & 1u) * 3u) << (2 * n1);
+    idx ^= lomask_n2;
+    cf z = lut[idx & (L::ENTRIES - 1)];
+    if (L::NG > 1) z = cadd(z, lut[L::ENTRIES + (idx >> (2 * L::GS))]);
+    return z;
+}
+
 }  // namespace ga

@@ -99,12 +99,6 @@ struct RealSrc {      // SearchInit(): real replica, imaginary part 0 (:101-102)
 // the same bits) and a sample group costs N1 byte loads, a few shifts and ONE table load instead of N1 unpack/select/
 // multiply-add chains.  The LO bits of the N1 samples of a group come packed from lomask[n2] (2 bits per sample), the
 // data bit is spread over both and XORed in.  N1 = 10 uses two groups of five (1024-entry tables).
-template <class G> struct FwdLut {
-    static constexpr int GS = G::N1 <= 5 ? G::N1 : 5, NG = (G::N1 + GS - 1) / GS;
-    static constexpr int ENTRIES = 1 << (2 * GS);
-    static constexpr int BYTES = NG * ENTRIES * (int)sizeof(cf);
-    static_assert(G::N2 % 8 == 0, "sample groups must sit at the same bit of their bytes");
-};
 #ifndef FWD_MINB
 #define FWD_MINB 2     // measured: 2 CTAs/SM at 126 registers beat 3 at 80 (spills)
 #endif
@@ -123,28 +117,15 @@ __global__ void __launch_bounds__(T, MODE == 0 ? FWD_MINB : 1) fwd_kernel(const 
     if (MODE == 0 && lomask != nullptr) {
         typedef FwdLut<G> L;
         cf *lut = sm + G::SMEM_ELEMS;
-        for (int e = threadIdx.x; e < L::NG * L::ENTRIES; e += T) {
-            const int g = e / L::ENTRIES, code = e - g * L::ENTRIES, first = g * L::GS;
-            const int last = first + L::GS < G::N1 ? first + L::GS : G::N1;
-            auto x = [&](int n1) { const int c = (code >> (2 * (n1 - first))) & 3; return mk((c & 1) ? -1.0f : 1.0f, (c & 2) ? -1.0f : 1.0f); };
-            cf z = first == 0 ? x(0) : cmul(x(first), k1s[first]);
-            for (int n1 = first + 1; n1 < last; n1++) cfma(z, x(n1), k1s[n1]);
-            lut[e] = z;
-        }
+        for (int e = threadIdx.x; e < L::NG * L::ENTRIES; e += T) lut[e] = fwd_lut_entry<G>(e, k1s);
         __syncthreads();
         const unsigned char *chunk = bits + (size_t)item * chunk_bytes;
         for (int j = threadIdx.x; j < G::NA; j += T) {
             cf p[G::RA];
 #pragma unroll
             for (int a = 0; a < G::RA; a++) {
-                const int n2 = a * G::NA + j, sh = n2 & 7;
-                const unsigned char *b = chunk + (n2 >> 3);
-                unsigned idx = 0;
-#pragma unroll
-                for (int n1 = 0; n1 < G::N1; n1++) idx |= (((unsigned)b[n1 * (G::N2 / 8)] >> sh) & 1u) * 3u << (2 * n1);
-                idx ^= lomask[n2];
-                cf z = lut[idx & (L::ENTRIES - 1)];
-                if (L::NG > 1) z = cadd(z, lut[L::ENTRIES + (idx >> (2 * L::GS))]);
+                const int n2 = a * G::NA + j;
+                const cf z = fwd_lut_gather<G>(chunk, n2, lomask[n2], lut);
                 p[a] = (s == 0) ? z : cmul(z, tw_load<-1>(tw, n2 * s));
             }
             passA_finish<G, -1>(p, j, 0, tw, sm);

@@ -99,6 +99,41 @@ static void emu_fwd_t(const cf *x, int s, cf *out)
     }
 }
 
+// Pass-A input of Sample() from packed bits, sample by sample (what BitSrc does in fwd_kernel, c/search_offline.cpp:143-153)
+// or through the sample-group tables (fwd_lut_entry / fwd_lut_gather, ga_fft3.h): out[a*NA + j] = the value pass A feeds
+// its radix-RA butterfly with, before the n2*s twiddle.
+struct BitSrcHost {
+    const unsigned char *chunk, *lo;
+    cf operator()(int n) const
+    {
+        const int bit = (chunk[n >> 3] >> (n & 7)) & 1, l = lo[n];
+        return mk((bit ^ (l & 1)) ? -1.0f : 1.0f, (bit ^ (l >> 1)) ? -1.0f : 1.0f);
+    }
+};
+template <class G>
+static void emu_gather_t(const unsigned char *chunk, const unsigned char *lo, int s, int use_lut, cf *out)
+{
+    std::vector<cf> k1 = make_k1tab<G>();
+    const cf *k1s = k1.data() + (size_t)s * G::N1;
+    if (!use_lut) {
+        BitSrcHost src{chunk, lo};
+        for (int n2 = 0; n2 < G::N2; n2++) {
+            cf z = src(n2);
+            for (int n1 = 1; n1 < G::N1; n1++) cfma(z, src(G::N2 * n1 + n2), k1s[n1]);      // as fwd_passA
+            out[n2] = z;
+        }
+        return;
+    }
+    typedef FwdLut<G> L;
+    std::vector<cf> lut((size_t)L::NG * L::ENTRIES);
+    for (int e = 0; e < L::NG * L::ENTRIES; e++) lut[e] = fwd_lut_entry<G>(e, k1s);
+    for (int n2 = 0; n2 < G::N2; n2++) {
+        unsigned lm = 0;
+        for (int n1 = 0; n1 < G::N1; n1++) lm |= (unsigned)(lo[(size_t)G::N2 * n1 + n2] & 3) << (2 * n1);   // as create_impl (gpsacq.cu)
+        out[n2] = fwd_lut_gather<G>(chunk, n2, lm, lut.data());
+    }
+}
+
 // ---- native W-point prime-factor transforms (ga_pfa.h), thread by thread like pfa_fwd_kernel / pfa_cell_kernel
 template <class G>
 static void emu_pfa_fwd_t(const cf *x, int conj, cf *out)
@@ -241,6 +276,16 @@ int emu_pfa_cell(int w, const float *xs, const float *cs, int q, float *y, float
 }
 
 // x: N complex time samples; out: N2 values X[N1*q+s]
+int emu_gather(int id, const unsigned char *chunk, const unsigned char *lo, int s, int use_lut, float *out)
+{
+    switch (id) {
+    case 0: emu_gather_t<G8000>(chunk, lo, s, use_lut, (cf *)out); return 0;
+    case 1: emu_gather_t<G10000>(chunk, lo, s, use_lut, (cf *)out); return 0;
+    case 2: emu_gather_t<G4000>(chunk, lo, s, use_lut, (cf *)out); return 0;
+    }
+    return -1;
+}
+
 int emu_fwd(int id, const float *x, int s, float *out)
 {
     switch (id) {

@@ -145,6 +145,36 @@ def _emu():
     return L
 
 
+@pytest.mark.parametrize("gid", [0, 1, 2])
+def test_forward_gather_tables_replay(gid):
+    """fwd_kernel's table-driven pass-A input (ga_fft3.h fwd_lut_entry / fwd_lut_gather, one table load per group of N1
+    one-bit samples) against the sample-by-sample unpack + XOR mix + multiply-add of Sample() (c/search_offline.cpp:143-153)
+    on random bits and a random LO table: bit-identical for N1 = 5 and N1 = 4 (same operation order), float rounding
+    only for N1 = 10 (two groups of five, summed)."""
+    L = _emu()
+    n1, n2 = ctypes.c_int(), ctypes.c_int()
+    assert L.emu_geom(gid, ctypes.byref(n1), ctypes.byref(n2)) == 0
+    N1, N2 = n1.value, n2.value
+    rng = np.random.default_rng(100 + gid)
+    chunk = rng.integers(0, 256, 5120, dtype=np.uint8)
+    lo = rng.integers(0, 4, 40960, dtype=np.uint8)
+    up = ctypes.POINTER(ctypes.c_ubyte)
+    fp = ctypes.POINTER(ctypes.c_float)
+    for s in range(N1):
+        a, b = np.zeros(N2, np.complex64), np.zeros(N2, np.complex64)
+        assert L.emu_gather(gid, chunk.ctypes.data_as(up), lo.ctypes.data_as(up), s, 0, a.ctypes.data_as(fp)) == 0
+        assert L.emu_gather(gid, chunk.ctypes.data_as(up), lo.ctypes.data_as(up), s, 1, b.ctypes.data_as(fp)) == 0
+        if N1 <= 5:
+            assert a.tobytes() == b.tobytes(), f"s={s}"
+        else:
+            assert np.abs(a - b).max() <= 2e-6 * np.abs(a).max()
+        # and against the definition in double
+        bits = ((chunk[:, None] >> np.arange(8)) & 1).reshape(-1)[: N1 * N2].astype(np.int64)
+        x = np.where(bits ^ (lo[: N1 * N2] & 1), -1.0, 1.0) + 1j * np.where(bits ^ (lo[: N1 * N2] >> 1), -1.0, 1.0)
+        z = (x.reshape(N1, N2) * np.exp(-2j * np.pi * np.arange(N1) * s / N1)[:, None]).sum(0)
+        assert np.abs(b - z).max() <= 1e-5
+
+
 # gid 0-2: the three REF geometries (N = 40000); 3: a GRID embedding geometry (N1 = 2, L = 12800); 4: a GRID exact-length
 # geometry (N1 = 1, L = W = 4096)
 @pytest.mark.parametrize("gid,W", [(0, 5456), (1, 8184), (2, 2800), (3, 5456), (4, 4096)])

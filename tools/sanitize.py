@@ -12,6 +12,14 @@ data = (ROOT / "tests/golden/nottingham_fs5456_if4092_runs0-3.bin").read_bytes()
 with ga.Acquisition(4.092e6, 5.456e6, max_blocks=8) as a:
     pk = a.search_blocks(data[: 11 * 5120])
     print("REF", pk["lo_shift"][:4], pk["ca_shift"][:4])
+os.environ["GPSACQ_CELL_TMA"] = "1"            # the TMA-staged REF cell kernel (ga_cell_tma.cuh): mbarrier ring, UTMALDG
+with ga.Acquisition(4.092e6, 5.456e6, max_blocks=8) as a:
+    pk2 = a.search_blocks(data[: 11 * 5120])
+    print("REF tma", a.info["cell_threads"], bool((pk2["ca_shift"] == pk["ca_shift"]).all()))
+os.environ["GPSACQ_CELL_TMA"] = "0"
+with ga.Acquisition(16.368e6 / 4, 16.368e6, max_blocks=2) as a:      # FS > 10 MHz: segmented windows
+    pk3 = a.search_blocks(data[: 2 * 5120])
+    print("REF 16.368", pk3["ca_shift"][:2])
 with ga.Acquisition(2.046e6, 8.184e6, max_blocks=4) as a:
     pk = a.search_blocks((ROOT / "tests/golden/gps_sig_fs8184_if2046_runs0-1.bin").read_bytes()[: 5 * 5120])
     print("REF 8.184", pk["lo_shift"][:4])
