@@ -9,15 +9,47 @@
 
 namespace ga {
 
-// pass 1: exact integer sums of I and Q (format 0: uint8 offset 128, format 1: int8)
+// pass 1: exact integer sums of I and Q (format 0: uint8 offset 128, format 1: int8).  The stream is read with 128-bit
+// loads (iq 16-byte aligned: eight samples per load) and the byte lanes are summed with dp4a -- mask 0x00010001 picks the
+// two I bytes of a 32-bit word, 0x01000100 the two Q bytes; the 32-bit partial sums are flushed to 64 bits every 1024
+// loads (at most 1024 * 8 * 255 < 2^31).  The offset 128 of the unsigned format comes off once at the end.
 __global__ void iq8_sum_kernel(const unsigned char *__restrict__ iq, size_t n_samples, int format,
                                long long *__restrict__ sums /* [2] */)
 {
     long long si = 0, sq = 0;
-    for (size_t n = (size_t)blockIdx.x * blockDim.x + threadIdx.x; n < n_samples; n += (size_t)gridDim.x * blockDim.x) {
-        const int a = iq[2 * n], b = iq[2 * n + 1];
-        si += format == 0 ? a - 128 : (int)(signed char)a;
-        sq += format == 0 ? b - 128 : (int)(signed char)b;
+    const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x, nthr = (size_t)gridDim.x * blockDim.x;
+    if ((reinterpret_cast<uintptr_t>(iq) & 15) == 0) {
+        const size_t n16 = n_samples / 8;                                 // whole groups of 8 samples = 16 bytes
+        const uint4 *v = reinterpret_cast<const uint4 *>(iq);
+        int ai = 0, aq = 0, since = 0;
+        for (size_t g = tid; g < n16; g += nthr) {
+            const uint4 x = __ldg(v + g);
+            if (format == 0) {
+                ai = (int)__dp4a(x.x, 0x00010001u, (unsigned)ai); aq = (int)__dp4a(x.x, 0x01000100u, (unsigned)aq);
+                ai = (int)__dp4a(x.y, 0x00010001u, (unsigned)ai); aq = (int)__dp4a(x.y, 0x01000100u, (unsigned)aq);
+                ai = (int)__dp4a(x.z, 0x00010001u, (unsigned)ai); aq = (int)__dp4a(x.z, 0x01000100u, (unsigned)aq);
+                ai = (int)__dp4a(x.w, 0x00010001u, (unsigned)ai); aq = (int)__dp4a(x.w, 0x01000100u, (unsigned)aq);
+                ai -= 8 * 128; aq -= 8 * 128;
+            } else {
+                ai = __dp4a((int)x.x, 0x00010001, ai); aq = __dp4a((int)x.x, 0x01000100, aq);
+                ai = __dp4a((int)x.y, 0x00010001, ai); aq = __dp4a((int)x.y, 0x01000100, aq);
+                ai = __dp4a((int)x.z, 0x00010001, ai); aq = __dp4a((int)x.z, 0x01000100, aq);
+                ai = __dp4a((int)x.w, 0x00010001, ai); aq = __dp4a((int)x.w, 0x01000100, aq);
+            }
+            if (++since == 1024) { si += ai; sq += aq; ai = aq = since = 0; }
+        }
+        si += ai; sq += aq;
+        for (size_t n = n16 * 8 + tid; n < n_samples; n += nthr) {         // the last n_samples % 8 samples
+            const int a = iq[2 * n], b = iq[2 * n + 1];
+            si += format == 0 ? a - 128 : (int)(signed char)a;
+            sq += format == 0 ? b - 128 : (int)(signed char)b;
+        }
+    } else {
+        for (size_t n = tid; n < n_samples; n += nthr) {
+            const int a = iq[2 * n], b = iq[2 * n + 1];
+            si += format == 0 ? a - 128 : (int)(signed char)a;
+            sq += format == 0 ? b - 128 : (int)(signed char)b;
+        }
     }
 #pragma unroll
     for (int off = 16; off > 0; off >>= 1) {
@@ -58,34 +90,51 @@ __global__ void iq8_to_bits_kernel(const unsigned char *__restrict__ iq, size_t 
 // table[(p*n) mod q] (double cos/sin made on the host in long double) -- no double-precision sincos of a large
 // argument per sample.  The mathematically exact phase; the MATLAB expression differs from it by its own rounding of
 // 2*pi*fc*n/fs (~1e-10 rad at n ~ 1e8), which matters only where |r| is that small.
+// One thread per FOUR output bytes: 32 samples = four 128-bit loads in, one 32-bit store out (d_bits is 4-byte aligned:
+// it comes from cudaMalloc or from the caller's device buffer at a multiple of 32 samples); the phasor table sits in
+// shared memory when it is small (the usual front-end ratios give q of a few hundred).
 __global__ void iq8_to_bits_table_kernel(const unsigned char *__restrict__ iq, size_t n_samples, size_t n0, int format,
                                          double mean_i, double mean_q, const double2 *__restrict__ table,
                                          unsigned long long p, unsigned long long q, unsigned char *__restrict__ bits)
 {
-    const size_t byte = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (byte * 8 >= n_samples) return;
-    unsigned long long k = (((n0 + byte * 8) % q) * p) % q;            // p, q < 2^31: no overflow
+    extern __shared__ double2 tab_s[];
+    const bool in_smem = q <= 2048;
+    if (in_smem) {
+        for (unsigned k = threadIdx.x; k < (unsigned)q; k += blockDim.x) tab_s[k] = table[k];
+        __syncthreads();
+    }
+    const double2 *tab = in_smem ? tab_s : table;
+    const size_t word = (size_t)blockIdx.x * blockDim.x + threadIdx.x;    // output word = samples 32*word .. 32*word+31
+    if (word * 32 >= n_samples) return;
+    unsigned long long k = (((n0 + word * 32) % q) * p) % q;               // p, q < 2^31: no overflow
+    const bool whole = word * 32 + 32 <= n_samples && (reinterpret_cast<uintptr_t>(bits) & 3) == 0;
     unsigned out = 0;
-    // 16 input bytes per thread: one 128-bit load when the whole group is inside the buffer
-    unsigned char raw[16];
-    if (byte * 8 + 8 <= n_samples) {
-        const uint4 v = *reinterpret_cast<const uint4 *>(iq + 16 * byte);
-        *reinterpret_cast<uint4 *>(raw) = v;
-    } else {
-        for (int i = 0; i < 16; i++) raw[i] = (byte * 16 + i < 2 * n_samples) ? iq[16 * byte + i] : 0;
-    }
 #pragma unroll
-    for (int j = 0; j < 8; j++) {
-        if (byte * 8 + j >= n_samples) break;
-        const int a = raw[2 * j], b = raw[2 * j + 1];
-        const double yi = (format == 0 ? a - 128 : (int)(signed char)a) - mean_i;
-        const double yq = (format == 0 ? b - 128 : (int)(signed char)b) - mean_q;
-        const double2 cs = table[k];
-        const double r = yi * cs.x - yq * cs.y;
-        out |= (r < 0.0 ? 1u : 0u) << j;
-        k += p; if (k >= q) k -= q;
+    for (int g = 0; g < 4; g++) {                                          // output byte g of the word
+        const size_t byte = word * 4 + g;
+        if (byte * 8 >= n_samples) break;
+        unsigned char raw[16];
+        if (byte * 8 + 8 <= n_samples) {
+            *reinterpret_cast<uint4 *>(raw) = __ldg(reinterpret_cast<const uint4 *>(iq + 16 * byte));
+        } else {
+            for (int i = 0; i < 16; i++) raw[i] = (byte * 16 + i < 2 * n_samples) ? iq[16 * byte + i] : 0;
+        }
+        unsigned ob = 0;
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+            if (byte * 8 + j >= n_samples) break;
+            const int a = raw[2 * j], b = raw[2 * j + 1];
+            const double yi = (format == 0 ? a - 128 : (int)(signed char)a) - mean_i;
+            const double yq = (format == 0 ? b - 128 : (int)(signed char)b) - mean_q;
+            const double2 cs = tab[k];
+            const double r = yi * cs.x - yq * cs.y;
+            ob |= (r < 0.0 ? 1u : 0u) << j;
+            k += p; if (k >= q) k -= q;
+        }
+        if (whole) out |= ob << (8 * g);
+        else bits[byte] = (unsigned char)ob;
     }
-    bits[byte] = (unsigned char)out;
+    if (whole) reinterpret_cast<unsigned *>(bits)[word] = out;
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -97,6 +146,8 @@ __global__ void iq8_to_bits_table_kernel(const unsigned char *__restrict__ iq, s
 // table lo[k] = lo_sin | lo_cos << 1; sample i uses k = i (i < mu) or mu + (i - mu) mod lambda.
 // One thread per input byte: 8 samples -> 16 output bytes, one 128-bit store.
 // ---------------------------------------------------------------------------------------------------------------
+// (The LO table is allocated with 16 spare bytes: the eight codes of a thread are cut out of three aligned 32-bit loads
+// with two funnel shifts instead of eight byte loads; the group that wraps around the period takes the byte path.)
 __global__ void bits_to_iq8_kernel(const unsigned char *__restrict__ bits, size_t n_bytes, size_t first_sample,
                                    const unsigned char *__restrict__ lo, unsigned long long mu, unsigned long long lambda,
                                    int amp, uint4 *__restrict__ out)
@@ -105,15 +156,28 @@ __global__ void bits_to_iq8_kernel(const unsigned char *__restrict__ bits, size_
         const unsigned long long i0 = first_sample + 8ull * byte;
         unsigned long long k = i0 < mu ? i0 : mu + (i0 - mu) % lambda;
         const unsigned b = bits[byte];
+        unsigned l03, l47;                                                        // LO codes of samples 0..3 and 4..7, one per byte
+        if (k + 8 <= mu + lambda) {
+            const unsigned *w = reinterpret_cast<const unsigned *>(lo + (k & ~3ull));
+            const unsigned w0 = __ldg(w), w1 = __ldg(w + 1), w2 = __ldg(w + 2), sh = 8u * (unsigned)(k & 3);
+            l03 = __funnelshift_r(w0, w1, sh); l47 = __funnelshift_r(w1, w2, sh);
+        } else {
+            l03 = l47 = 0;
+#pragma unroll
+            for (int j = 0; j < 8; j++) {
+                const unsigned l = lo[k];
+                if (j < 4) l03 |= l << (8 * j); else l47 |= l << (8 * (j - 4));
+                k++; if (k == mu + lambda) k = mu;
+            }
+        }
         unsigned w[4];
 #pragma unroll
         for (int j = 0; j < 8; j++) {
-            const unsigned l = lo[k];
+            const unsigned l = ((j < 4 ? l03 : l47) >> (8 * (j & 3))) & 3u;
             const unsigned bit = (b >> j) & 1u;                                   // LSB first (:66-67)
             const int vi = (bit ^ (l & 1u)) ? -amp : amp, vq = (bit ^ (l >> 1)) ? -amp : amp;
             const unsigned pair = ((unsigned)vi & 0xFFu) | (((unsigned)vq & 0xFFu) << 8);
             if (j & 1) w[j >> 1] |= pair << 16; else w[j >> 1] = pair;
-            k++; if (k == mu + lambda) k = mu;
         }
         out[byte] = make_uint4(w[0], w[1], w[2], w[3]);
     }

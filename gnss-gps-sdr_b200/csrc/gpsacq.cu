@@ -1127,7 +1127,9 @@ static int iq8_convert_piece(gpsacq *h, const unsigned char *d_iq, size_t n, siz
             CUDA_TRY(h, cudaMemcpy(h->d_iq_tab, tab.data(), 2 * q * sizeof(double), cudaMemcpyHostToDevice));
             h->iq_tab_p = p; h->iq_tab_q = q; h->iq_tab_neg = shift_hz < 0;
         }
-        iq8_to_bits_table_kernel<<<(unsigned)((nbytes + 255) / 256), 256, 0, h->stream>>>(d_iq, n, n0, format, mi, mq, (const double2 *)h->d_iq_tab, p, q, d_bits);
+        const size_t nwords = (nbytes + 3) / 4;                  // one thread per 32 samples
+        const size_t tab_smem = q <= 2048 ? (size_t)q * sizeof(double2) : 0;
+        iq8_to_bits_table_kernel<<<(unsigned)((nwords + 255) / 256), 256, tab_smem, h->stream>>>(d_iq, n, n0, format, mi, mq, (const double2 *)h->d_iq_tab, p, q, d_bits);
     } else {
         iq8_to_bits_kernel<<<(unsigned)((nbytes + 255) / 256), 256, 0, h->stream>>>(d_iq, n, n0, format, mi, mq, shift_hz, fs, d_bits);
     }
@@ -1201,7 +1203,7 @@ static int conv_prepare(int device, double fc, double fs, unsigned long long n_n
     LoCycle c;
     if (!conv_lo_cycle(fc, fs, n_needed, c)) { g_create_error = "bits_to_iq8: 4*fc/fs must lie in [0,4) and the input be shorter than 2^27 samples when the LO recurrence has no short cycle"; return GPSACQ_EINVAL; }
     if (g_conv.d_lo) { cudaFree(g_conv.d_lo); g_conv.d_lo = nullptr; }
-    if (cudaMalloc(&g_conv.d_lo, c.tab.size()) != cudaSuccess || cudaMemcpy(g_conv.d_lo, c.tab.data(), c.tab.size(), cudaMemcpyHostToDevice) != cudaSuccess) {
+    if (cudaMalloc(&g_conv.d_lo, c.tab.size() + 16) != cudaSuccess || cudaMemset(g_conv.d_lo, 0, c.tab.size() + 16) != cudaSuccess || cudaMemcpy(g_conv.d_lo, c.tab.data(), c.tab.size(), cudaMemcpyHostToDevice) != cudaSuccess) {
         g_create_error = "bits_to_iq8: LO table upload failed"; return GPSACQ_ECUDA;
     }
     g_conv.device = device; g_conv.fc = fc; g_conv.fs = fs; g_conv.cyc = std::move(c);

@@ -364,6 +364,24 @@ def test_tma_staged_kernel_matches_ldg_kernel(ga, monkeypatch):
     compare_peaks(got, gold)
 
 
+def test_pinned_and_pageable_host_buffers_agree(ga, engines):
+    """gpsacq_search_blocks() hands a page-locked caller buffer straight to the copy engine and stages pageable memory
+    through its own pinned buffer; the batch is cut into 1/8, 1/8, 1/4, 1/2 slices either way.  Same records, also
+    for an unaligned view into the pinned buffer and a ragged chunk count."""
+    import torch
+    c = CAPTURES["nottingham"]
+    raw = np.frombuffer(c["bin"].read_bytes(), np.uint8)
+    data = np.concatenate([raw, raw, raw])[: 331 * 5120]            # 331 chunks: four unequal slices
+    acq = engines(c["fc"], c["fs"])
+    want = acq.search_blocks(data.copy()).copy()
+    pinned = torch.empty(data.size + 5120, dtype=torch.uint8).pin_memory()
+    view = pinned.numpy()[5120:]
+    view[:] = data
+    got = acq.search_blocks(view)
+    assert got.tobytes() == want.tobytes()
+    assert np.array_equal(want["sv"], np.arange(331) % 32)
+
+
 # ---- device-pointer API on torch's stream ---------------------------------------------------------------
 def test_device_api_on_torch_stream(ga, engines):
     import torch
