@@ -90,6 +90,15 @@ enum { XID_10000 = 7, XID_8000 = 8, XID_4000 = 9, XID_4096 = 10, XID_2048 = 11 }
 #ifndef PFA_B_8184
 #define PFA_B_8184 3
 #endif
+#ifndef PFA_T_8184_K1
+#define PFA_T_8184_K1 PFA_T_8184      // K = 1 handles (no tensor memory): their own CTA shape
+#endif
+#ifndef PFA_T_5456_K1
+#define PFA_T_5456_K1 PFA_T_5456
+#endif
+#ifndef PFA_B_5456_K1
+#define PFA_B_5456_K1 PFA_B_5456
+#endif
 #ifndef PFA_T_2800
 #define PFA_T_2800 128
 #endif
@@ -664,8 +673,8 @@ template <class G, int T, int MINB, bool MULTI> struct PfaOps {
 };
 
 #define PFA_DISPATCH(h, CALL)                                                                               \
-    (h->gid == PID_5456   ? (h->kblocks > 1 ? PfaOps<P5456, PFA_T_5456, PFA_B_5456, true>::CALL : PfaOps<P5456, PFA_T_5456, PFA_B_5456, false>::CALL) \
-     : h->gid == PID_8184 ? (h->kblocks > 1 ? PfaOps<P8184, PFA_T_8184, PFA_B_8184, true>::CALL : PfaOps<P8184, PFA_T_8184, PFA_B_8184, false>::CALL) \
+    (h->gid == PID_5456   ? (h->kblocks > 1 ? PfaOps<P5456, PFA_T_5456, PFA_B_5456, true>::CALL : PfaOps<P5456, PFA_T_5456_K1, PFA_B_5456_K1, false>::CALL) \
+     : h->gid == PID_8184 ? (h->kblocks > 1 ? PfaOps<P8184, PFA_T_8184, PFA_B_8184, true>::CALL : PfaOps<P8184, PFA_T_8184_K1, PFA_B_8184, false>::CALL) \
                           : (h->kblocks > 1 ? PfaOps<P2800, PFA_T_2800, PFA_B_2800, true>::CALL : PfaOps<P2800, PFA_T_2800, PFA_B_2800, false>::CALL))
 
 #define GRID_DISPATCH(h, CALL)                                                                              \
