@@ -1572,6 +1572,12 @@ int gpsacq_group_search_blocks(gpsacq_group_t *g, const uint8_t *bits, size_t n_
     DeviceGuard guard;
     if (!g || (!bits && n_blocks) || (!out && n_blocks)) return GPSACQ_EINVAL;
     const size_t ng = g->eng.size(), per_batch = (size_t)g->cap * ng;
+    bool pinned = false;
+    {
+        cudaPointerAttributes attr;
+        if (cudaPointerGetAttributes(&attr, bits) == cudaSuccess) pinned = attr.type == cudaMemoryTypeHost;
+        else cudaGetLastError();
+    }
     for (size_t done = 0; done < n_blocks;) {
         const size_t nb = std::min(per_batch, n_blocks - done);
         // contiguous, balanced ranges of this batch; chunk b of the stream keeps PRN b mod 32
@@ -1582,9 +1588,12 @@ int gpsacq_group_search_blocks(gpsacq_group_t *g, const uint8_t *bits, size_t n_
             const size_t n = lo[d + 1] - lo[d];
             if (cudaSetDevice(h->device) != cudaSuccess) { g->err = "cudaSetDevice failed"; return GPSACQ_ECUDA; }
             if (n == 0) continue;
-            memcpy(h->h_bits, bits + (done + lo[d]) * (size_t)h->chunk_bytes, n * (size_t)h->chunk_bytes);
+            // a page-locked caller buffer goes straight to the copy engine (every device starts at once); pageable memory
+            // is staged through the engine's pinned buffer, device after device
+            const unsigned char *src = bits + (done + lo[d]) * (size_t)h->chunk_bytes;
+            if (!pinned) { memcpy(h->h_bits, src, n * (size_t)h->chunk_bytes); src = h->h_bits; }
             for (size_t b = 0; b < n; b++) h->h_sv[b] = (int)((done + lo[d] + b) % GPSACQ_NUM_SATS);
-            if (cudaMemcpyAsync(h->d_bits, h->h_bits, n * (size_t)h->chunk_bytes, cudaMemcpyHostToDevice, h->stream) != cudaSuccess ||
+            if (cudaMemcpyAsync(h->d_bits, src, n * (size_t)h->chunk_bytes, cudaMemcpyHostToDevice, h->stream) != cudaSuccess ||
                 cudaMemcpyAsync(h->d_sv, h->h_sv, n * sizeof(int), cudaMemcpyHostToDevice, h->stream) != cudaSuccess) { g->err = "H2D copy failed"; return GPSACQ_ECUDA; }
             const int rc = gpsacq_search_blocks_device(h, h->d_bits, n, h->d_sv, (gpsacq_peak *)h->d_peaks);
             if (rc) { g->err = h->err; return rc; }
