@@ -315,7 +315,14 @@ __global__ void __launch_bounds__(T, cell_minb(T)) cell_kernel_tm(const cf *__re
     // this warp's private window: lanes 32*(wid%4).., columns (wid/4)*COL_SLOT..
     const uint32_t tm_mine = tm_base + ((32u * (uint32_t)(wid & 3)) << 16) + (uint32_t)(wid >> 2) * COL_SLOT;
     const uint32_t tm_second = FIVE ? tm_base2_s : 0u;      // fifth warp, second task (lanes 0..31 of the 32-column allocation)
+    // Five warps: the hardware puts warps 0 and 4 of a CTA on the same SM sub-partition, and the three co-resident CTAs on
+    // three different ones (tools/ubench/warpmap.cu with 160 threads).  The two warps that get only two tasks per pass are
+    // therefore warps 0 and 4: every CTA loads its sub-partitions 4/3/3/3 and the SM 10/10/10/9 (warps 3 and 4: 10/10/11/8).
+#ifdef GA_VW_OLD
     const int vw = wid;
+#else
+    const int vw = FIVE ? (wid + 4) % 5 : wid;
+#endif
 
     // Cells are handed out in ascending order by a device-wide ticket counter (sched[0]; the first gridDim.x tickets are
     // the CTA numbers): whichever CTA finishes takes the next cell, so the CTAs of a launch work on a narrow window of

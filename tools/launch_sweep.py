@@ -14,7 +14,7 @@ nb = int(sys.argv[1]) if len(sys.argv) > 1 else 3584
 subs = [int(x) for x in sys.argv[2].split(",")] if len(sys.argv) > 2 else [128, 512, 3584]
 if len(sys.argv) > 3 and sys.argv[3] == "static":
     os.environ["GPSACQ_STATIC_SCHED"] = "1"
-fc, fs = 4.092e6, 5.456e6
+fc, fs = float(os.environ.get("SWEEP_FC", 4.092e6)), float(os.environ.get("SWEEP_FS", 5.456e6))
 dev = torch.device("cuda", 0)
 rng = np.random.default_rng(0)
 d_bits = torch.from_numpy(rng.integers(0, 256, nb * 5120, dtype=np.uint8)).to(dev)
@@ -36,8 +36,8 @@ for sub in subs:
     torch.cuda.synchronize(dev)
     ms = e0.elapsed_time(e1) / reps
     pk = np.frombuffer(d_out.cpu().numpy().tobytes(), ga.PEAK_DTYPE)
-    print("%s %s sub=%d: %.3f ms per %d chunks -> %.3f Mcorr/s (contract frac %.3f)  last launch cells %.3f ms fwd %.3f ms  checksum %.6e" % (
-        os.environ.get("GPSACQ_LIB", "default"), "static" if os.environ.get("GPSACQ_STATIC_SCHED") else "ticket", sub, ms, nb,
+    print("%s %s fs=%.4g T=%d sub=%d: %.3f ms per %d chunks -> %.3f Mcorr/s (contract frac %.3f)  last launch cells %.3f ms fwd %.3f ms  checksum %.6e" % (
+        os.environ.get("GPSACQ_LIB", "default"), "static" if os.environ.get("GPSACQ_STATIC_SCHED") else "ticket", fs, acq.info["cell_threads"], sub, ms, nb,
         nb * acq.n_doppler / ms / 1e3, nb * acq.n_doppler / ms * 1e3 * 640016 / 6550.1e9, acq.stage_times()["cells_ms"], acq.stage_times()["fwd_ms"],
         float(pk["snr"].astype(np.float64).sum())), flush=True)
     acq.close()
