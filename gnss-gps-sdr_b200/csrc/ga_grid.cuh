@@ -75,7 +75,8 @@ __global__ void grid_replica_extend_kernel(const float *__restrict__ code_w, int
 template <class G, int T, int NW, int GID>
 __global__ void __launch_bounds__(T, TM_MINB) grid_cell_kernel(const cf *__restrict__ xg, const cf *__restrict__ cext,
                                                                const cf *__restrict__ tw, int n_cells, int n_dop, int kblocks,
-                                                               int wlen, int dmax, int n_base, CellStat *__restrict__ cells)
+                                                               int wlen, int dmax, int n_base, CellStat *__restrict__ cells,
+                                                               int *__restrict__ sched = nullptr)
 {
     static_assert(T % 32 == 0, "tcgen05.ld/st are warp-collective: whole warps only");
     constexpr int NWARP = T / 32;
@@ -93,6 +94,7 @@ __global__ void __launch_bounds__(T, TM_MINB) grid_cell_kernel(const cf *__restr
     __shared__ float red_best[NWARP], red_sum[NWARP];
     __shared__ int red_idx[NWARP];
     __shared__ uint32_t tm_base_s;
+    __shared__ int next_cell_s;
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
 
     if (wid == 0) {
@@ -105,7 +107,9 @@ __global__ void __launch_bounds__(T, TM_MINB) grid_cell_kernel(const cf *__restr
     const uint32_t tm_base = tm_base_s;
     const uint32_t tm_mine = tm_base + ((32u * (uint32_t)(wid & 3)) << 16) + (uint32_t)(wid >> 2) * COL_SLOT;
 
-    for (int cell = blockIdx.x; cell < n_cells; cell += gridDim.x) {
+    // cells in ascending order from the device-wide ticket counter, as in cell_kernel_tm / pfa_cell_kernel
+    int next_cell = 0;
+    for (int cell = blockIdx.x; cell < n_cells; cell = next_cell) {
         const int acq = cell / (n_dop * 32), r = cell - acq * (n_dop * 32);
         const int di = r >> 5, prn = r & 31;
         const cf *cb = cext + (size_t)prn * (2 * G::N);
@@ -127,6 +131,7 @@ __global__ void __launch_bounds__(T, TM_MINB) grid_cell_kernel(const cf *__restr
 
         for (int k = 0; k < kblocks; k++) {
             const cf *xb = xg + ((size_t)(acq * kblocks + k) * xstride + xsel) * G::N;
+            if (k == kblocks - 1 && tid == 0) next_cell = sched ? (int)gridDim.x + atomicAdd(sched, 1) : cell + (int)gridDim.x;
             for (int s = 0; s < G::N1; s++) {
                 const cf *xs = xb + (size_t)s * G::N2;
                 const cf *cs = cb + (size_t)s * (2 * G::N2);
@@ -212,7 +217,9 @@ __global__ void __launch_bounds__(T, TM_MINB) grid_cell_kernel(const cf *__restr
             sum += os;
         }
         if (lane == 0) { red_best[wid] = best; red_idx[wid] = besti; red_sum[wid] = sum; }
+        if (tid == 0) next_cell_s = next_cell;
         __syncthreads();
+        next_cell = next_cell_s;          // thread 0 rewrites it only after the barriers of the next cell
         if (wid == 0) {
             best = lane < NWARP ? red_best[lane] : 0.0f;
             besti = lane < NWARP ? red_idx[lane] : 0x7fffffff;
@@ -234,6 +241,7 @@ __global__ void __launch_bounds__(T, TM_MINB) grid_cell_kernel(const cf *__restr
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     if (wid == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tm_base), "r"(TM_COLS) : "memory");
+    if (sched && tid == 0 && atomicAdd(sched + 1, 1) == (int)gridDim.x - 1) { sched[0] = 0; sched[1] = 0; }     // last CTA out rewinds
 }
 
 }  // namespace ga

@@ -604,7 +604,7 @@ template <class H, int T, int NW, int HID> struct GridOps {
         const int n_cells = (int)(n_acq * 32 * (size_t)h->ndop);
         const int grid = std::min(n_cells, h->cell_ctas);
         grid_cell_kernel<H, T, NW, HID><<<grid, T, h->cell_smem, h->stream>>>(h->d_xg, h->d_cext, h->d_tw, n_cells, h->ndop,
-                                                                            h->kblocks, h->w, h->dmax, h->n_base, h->d_cells);
+                                                                            h->kblocks, h->w, h->dmax, h->n_base, h->d_cells, h->d_sched);
         CUDA_TRY(h, cudaGetLastError());
         return 0;
     }

@@ -15,6 +15,7 @@ CONFIGS = {
     "C2": dict(fs=8.184e6, fc=2.046e6, max_fo=5000.0, step=500.0, K=1, n_acq=64),
     "C3": dict(fs=2.8e6, fc=0.62e6, max_fo=100000.0, step=250.0, K=10, n_acq=4),
     "C4": dict(fs=8.184e6, fc=2.046e6, max_fo=100000.0, step=100.0, K=10, n_acq=1),
+    "X10": dict(fs=10e6, fc=2.6e6, max_fo=5000.0, step=500.0, K=1, n_acq=64),     # the receiver's own rate (c/gps.h:23-24): exact-length W = 10000
 }
 peak = json.loads((ROOT / "MEASURED_PEAKS.json").read_text())["hbm_gbs"] if (ROOT / "MEASURED_PEAKS.json").exists() else 6650.0
 for name in (sys.argv[1:] or list(CONFIGS)):
