@@ -238,9 +238,16 @@ constexpr uint32_t pow2_at_least(uint32_t x, uint32_t p = 32) { return p >= x ? 
 
 // Task loop of a warp (task = 32 butterflies): unrolled when a warp has at most two tasks per pass; with more (the
 // 128-thread shape) NOT unrolled, or the compiler hoists every task's operand loads and spills.
-template <int IT, class F> __device__ __forceinline__ void for_tasks(F &&f)
+#ifndef GA_UNROLL_BC
+#define GA_UNROLL_BC 1      // the task loops of passes B and C (shared-memory operands) fully unrolled whatever their length:
+                            // +2.2 % with three tasks per warp (160-thread CTAs; 128 registers, no spills)
+#endif
+#ifndef GA_UNROLL_A
+#define GA_UNROLL_A 0       // the same for pass A (global operands)
+#endif
+template <int IT, bool FORCE = false, class F> __device__ __forceinline__ void for_tasks(F &&f)
 {
-    if constexpr (IT <= 2) {
+    if constexpr (IT <= 2 || FORCE) {
 #pragma unroll
         for (int it = 0; it < IT; it++) f(it);
     } else {
@@ -347,18 +354,18 @@ __global__ void __launch_bounds__(T, cell_minb(T)) cell_kernel_tm(const cf *__re
             const cf *xs = xb + (size_t)s * G::N2;
             const cf *cs = cb + (size_t)sp * (2 * G::N2) + eoff;
             if (s == G::N1 - 1 && tid == 0) next_cell = sched ? (int)gridDim.x + atomicAdd(sched, 1) : cell + (int)gridDim.x;
-            for_tasks<ITA>([&](int it) {
+            for_tasks<ITA, GA_UNROLL_A != 0>([&](int it) {
                 const int jj = (vw + it * NWARP) * 32 + lane;
                 if (jj < G::NA) cell_passA<G>(GA_PERM_A ? passA_slot_to_j<G>(jj) : jj, s, xs, cs, tw, sm);
             });
             __syncthreads();
-            for_tasks<ITB>([&](int it) {
+            for_tasks<ITB, GA_UNROLL_BC != 0>([&](int it) {
                 const int j = (vw + it * NWARP) * 32 + lane;
                 if (j < G::NB) passB<G, +1>(j, s, tw, sm);
             });
             __syncthreads();
             const cf *ks = (SEG ? c_ktab_seg[seg] : c_ktab[GID]) + s * G::RC;
-            for_tasks<ITC>([&](int it) {
+            for_tasks<ITC, GA_UNROLL_BC != 0>([&](int it) {
                 const int task = vw + it * NWARP;
                 if (task < NTC) {          // warp-uniform
                     // every lane runs the butterfly (lanes past the end redo the last one) so that the
@@ -418,7 +425,13 @@ __global__ void __launch_bounds__(T, cell_minb(T)) cell_kernel_tm(const cf *__re
                 }
             });
             asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
-            __syncthreads();      // smem is rewritten by the next sub-sequence's pass A
+            // the tile is rewritten by the next sub-sequence's pass A; after the LAST sub-sequence the barrier of the
+            // per-cell reduction below does that job (one barrier less per cell)
+#ifdef GA_NO_BARRIER_MERGE
+            __syncthreads();
+#else
+            if (s < G::N1 - 1) __syncthreads();
+#endif
         }
 
 #pragma unroll

@@ -7,6 +7,16 @@
 #include "ga_grid.cuh"
 #include "ga_pfa.h"
 
+// Task loops of pfa_cell_kernel's passes B and C fully unrolled (pass A stays a rolled loop: its global operand loads would be
+// hoisted and spill).  Measured, ticket scheduler, M corr/s C1 / C2 / C3 / C4: rolled 61.6 / 38.8 / 171.9 / 43.4,
+// pass C unrolled 62.8 / 40.1 / 182.2 / 43.7, passes B and C 63.2 / 39.0 / 184.8 / 42.5 -- so pass C everywhere and pass B
+// except for W = 8184 (its 9 radix-31 tasks over 4 warps).
+#ifndef PFA_UNROLL_B
+#define PFA_UNROLL_B 1
+#endif
+#ifndef PFA_UNROLL_C
+#define PFA_UNROLL_C 1
+#endif
 #ifndef PFA_PIPE_A
 #define PFA_PIPE_A 0     // measured: software-pipelined pass A is 1-4 % SLOWER (the SM already overlaps the loads across its 12-16 warps)
 #endif
@@ -103,6 +113,7 @@ __global__ void __launch_bounds__(T, MINB) pfa_cell_kernel(const cf *__restrict_
     constexpr int NTA = cdiv(G::NA, 32), NTB = cdiv(G::NB, 32), NTC = cdiv(G::NC, 32);
     constexpr int ITA = cdiv(NTA, NWARP), ITB = cdiv(NTB, NWARP), ITC = cdiv(NTC, NWARP);
     constexpr bool PIPE_A = PFA_PIPE_A != 0;
+    constexpr int UNROLL_B = (PFA_UNROLL_B && G::W != 8184) ? ITB : 1, UNROLL_C = PFA_UNROLL_C ? ITC : 1;
     constexpr int NWP = (G::RC + 1) & ~1;                            // power accumulators per butterfly, even
     constexpr uint32_t COL_SLOT = (uint32_t)((ITC * NWP + 7) & ~7);
     constexpr uint32_t TM_COLS = pow2_at_least(COL_SLOT * cdiv(NWARP, 4));
@@ -177,13 +188,13 @@ __global__ void __launch_bounds__(T, MINB) pfa_cell_kernel(const cf *__restrict_
                 }
             }
             __syncthreads();
-#pragma unroll 1
+#pragma unroll UNROLL_B
             for (int it = 0; it < ITB; it++) {
                 const int j = (wid + it * NWARP) * 32 + lane;
                 if (j < G::NB) pfa_passB<G, +1>(j, sm);
             }
             __syncthreads();
-#pragma unroll 1
+#pragma unroll UNROLL_C
             for (int it = 0; it < ITC; it++) {
                 const int task = wid + it * NWARP;
                 if (task < NTC) {                                   // warp-uniform

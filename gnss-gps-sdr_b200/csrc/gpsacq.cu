@@ -115,7 +115,10 @@ enum { XID_10000 = 7, XID_8000 = 8, XID_4000 = 9, XID_4096 = 10, XID_2048 = 11 }
                             // Round 2, ticket scheduler, one B200: 160 x 3 9.00 M corr/s, 128 x 3 8.91, 256 x 2 8.91, 224 x 2 8.67,
                             // 448 x 2 8.53, 192 x 2 8.14
 #endif
-#define CELL_T_8000_WIDE 448  // search windows above 5600 samples (20 accumulators per butterfly): too many TMEM columns for 3 CTAs/SM
+#ifndef CELL_T_8000_WIDE
+#define CELL_T_8000_WIDE 256  // search windows above 5600 samples (20 accumulators per butterfly: too many TMEM columns for three CTAs per SM):
+                              // 256 x 2, 119 registers; the 448 x 2 shape of round 1 spilled (FS = 7 MHz: 6.83 -> 8.49 M corr/s)
+#endif
 #ifndef CELL_T_10000
 #define CELL_T_10000 256
 #endif
