@@ -1,10 +1,6 @@
 #!/bin/bash
 # round 2, session p: sub-partition balance A/B, then the full evidence run (tests, bench both arms, launch list, ncu captures)
 mkdir -p gpurun_out
-timeout 120 python tools/launch_sweep.py 3584 3584 2>&1 | grep -E "sub=|rror"
-GPSACQ_LIB=build/variants/vwold.so timeout 120 python tools/launch_sweep.py 3584 3584 2>&1 | grep -E "sub=|rror"
-timeout 120 python tools/launch_sweep.py 3584 3584 2>&1 | grep -E "sub=|rror"
-GPSACQ_LIB=build/variants/vwold.so timeout 120 python tools/launch_sweep.py 3584 3584 2>&1 | grep -E "sub=|rror"
 timeout 1200 python -m pytest tests -x -q -m gpu > gpurun_out/pytest_gpu.log 2>&1; echo "pytest rc=$?"; tail -4 gpurun_out/pytest_gpu.log
 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/smoke.log 2>&1; tail -1 gpurun_out/smoke.log
 python bench.py --steps 20 --warmup 3 > gpurun_out/bench_n1.json 2> gpurun_out/bench_n1.err; cut -c1-200 gpurun_out/bench_n1.json; tail -3 gpurun_out/bench_n1.err
