@@ -242,6 +242,9 @@ constexpr uint32_t pow2_at_least(uint32_t x, uint32_t p = 32) { return p >= x ? 
 #define GA_UNROLL_BC 1      // the task loops of passes B and C (shared-memory operands) fully unrolled whatever their length:
                             // +2.2 % with three tasks per warp (160-thread CTAs; 128 registers, no spills)
 #endif
+#ifndef GA_PEAK_BRANCHY
+#define GA_PEAK_BRANCHY 1   // peak tracking of pass C with data-dependent branches; 0: branch-free selects (measured 0.2 % slower)
+#endif
 #ifndef GA_UNROLL_A
 #define GA_UNROLL_A 0       // the same for pass A (global operands)
 #endif
@@ -394,6 +397,7 @@ __global__ void __launch_bounds__(T, cell_minb(T)) cell_kernel_tm(const cf *__re
                     };
                     // last sub-sequence: the outputs are complete -> power, first max, sum (:190-194)
                     auto peak = [&](const float (&a)[2 * NW]) {
+#if GA_PEAK_BRANCHY
 #pragma unroll
                         for (int w = 0; w < NW; w++) {
                             const int tau = tau0 + G::OUT_STRIDE * w;
@@ -403,6 +407,21 @@ __global__ void __launch_bounds__(T, cell_minb(T)) cell_kernel_tm(const cf *__re
                                 sum += pwr;
                             }
                         }
+#else
+                        // branch-free: same comparisons, same summation order; a lag outside the window takes part with
+                        // power -1 (never a maximum: powers are >= 0 and best starts at 0) and adds nothing to the sum
+#pragma unroll
+                        for (int w = 0; w < NW; w++) {
+                            const int tau = tau0 + G::OUT_STRIDE * w;
+                            const bool in = tau < wl;
+                            const float pwr = fmaf(a[2 * w], a[2 * w], a[2 * w + 1] * a[2 * w + 1]);
+                            const float cand = in ? pwr : -1.0f;
+                            const bool better = cand > best || (cand == best && tau < besti);
+                            best = better ? cand : best;
+                            besti = better ? tau : besti;
+                            sum = in ? sum + pwr : sum;
+                        }
+#endif
                     };
                     if constexpr (SPLIT_C) {
                         // store path and power path as separate code: their registers are allocated independently and
