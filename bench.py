@@ -10,11 +10,12 @@ semantics (N = 40000-point coherent window, 73 Doppler bins of fs/N = 136.4 Hz, 
 chunk per PRN; c/search_offline.cpp:176,239-246), because that is the only grid on which parity
 with gps_test is defined and the only one the reference arm can run.
 
-A "step" is one batch of 224 runs = 7168 chunks x 73 bins = 523,264 correlations per GPU (~60 ms, so
+A "step" is one batch of 224 runs = 7168 chunks x 73 bins = 523,264 correlations per GPU (~57 ms, so
 that 20 timed steps run for more than a second): forward FFT kernel, cell kernel (shifted conj-multiply
-+ pruned backward FFT + |.|^2 + peak), best-over-Doppler kernel -- launched per 128 chunks so that the block
-spectra stay in L2 between the forward and the cell launch -- and for N > 1 one NCCL all-gather of
-the 7168 32-byte peak records per rank -- inside the timed region of BOTH value and e2e.
++ pruned backward FFT + |.|^2 + peak), best-over-Doppler kernel -- ONE launch of each per step (the cell
+kernel's CTAs draw their cells from a device-wide ticket counter, so a block spectrum is fetched from HBM
+once and shared through L2 by its 73 cells however long the launch is) -- and for N > 1 one NCCL
+all-gather of the 7168 32-byte peak records per rank -- inside the timed region of BOTH value and e2e.
 Ranks work on different runs of the stream (weak scaling, no data-path collective).
 
 value   : device-resident inputs (packed bits already in HBM), CUDA events on the launching stream.
@@ -354,8 +355,8 @@ def run_engine(args, rank, world, local_rank):
             peak_gbs, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
         bpc = acq.info["bytes_per_corr"]
         cell_avg_ms = statistics.mean(cell_ms)
-        # a step is cut into launches of blocks_per_launch chunks (their block spectra stay in L2); the stage events
-        # bracket the last launch triple of a step
+        # a step is blocks_per_launch chunks per launch triple (the whole step unless GPSACQ_SUB_BLOCKS cuts it); the stage
+        # events bracket the last launch triple of a step
         launches_per_step = -(-nb // acq.info["blocks_per_launch"])
         corr_per_launch = acq.info["blocks_per_launch"] * ndop
         achieved = corr_per_launch * bpc / (cell_avg_ms * 1e-3) / 1e9
