@@ -34,6 +34,40 @@ __constant__ cf c_k1tab[NGEOM][K1TAB_MAX];
 constexpr int MAX_SEG = 4;
 __constant__ cf c_ktab_seg[MAX_SEG][KTAB_MAX];
 
+// ---- mbarrier / bulk-copy helpers (TMA): used by the forward kernel (1-D bulk copy of a chunk's bits) and by the TMA-staged
+// cell kernel (ga_cell_tma.cuh: 2-D tensor loads) -----------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
+{
+    asm volatile(
+        "{\n"
+        ".reg .pred P1;\n"
+        "LAB_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+        "@P1 bra DONE;\n"
+        "bra LAB_WAIT;\n"
+        "DONE:\n"
+        "}" ::"r"(bar), "r"(parity) : "memory");
+}
+// n bytes (a multiple of 16, source and destination 16-byte aligned) global -> shared, completion bytes on `bar` (SASS UBLKCP)
+__device__ __forceinline__ void bulk_load_1d(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+
 // ---------------------------------------------------------------------------------
 // C/A replica in the time domain.  One CTA per PRN.  chip_idx/blendA/blendB are the
 // code-NCO tables (functions of FS only) built on the host with the reference's
@@ -99,6 +133,10 @@ struct RealSrc {      // SearchInit(): real replica, imaginary part 0 (:101-102)
 // the same bits) and a sample group costs N1 byte loads, a few shifts and ONE table load instead of N1 unpack/select/
 // multiply-add chains.  The LO bits of the N1 samples of a group come packed from lomask[n2] (2 bits per sample), the
 // data bit is spread over both and XORed in.  N1 = 10 uses two groups of five (1024-entry tables).
+#ifndef GA_FWD_BULK
+#define GA_FWD_BULK 1       // forward kernel: stage the chunk's bits in shared memory with one TMA bulk copy (0: global byte loads)
+#endif
+constexpr int FWD_BITS_SMEM = 5120;      // a chunk: 10 packets of 512 bytes (c/search_offline.cpp:129,135-141)
 #ifndef FWD_MINB
 #define FWD_MINB 2     // measured: 2 CTAs/SM at 126 registers beat 3 at 80 (spills)
 #endif
@@ -117,9 +155,24 @@ __global__ void __launch_bounds__(T, MODE == 0 ? FWD_MINB : 1) fwd_kernel(const 
     if (MODE == 0 && lomask != nullptr) {
         typedef FwdLut<G> L;
         cf *lut = sm + G::SMEM_ELEMS;
+        // the chunk's packed bits (5120 bytes) are staged in shared memory by ONE bulk copy of the TMA engine
+        // (cp.async.bulk, SASS UBLKCP), issued before the tables are built and awaited after: pass A then reads its
+        // N1 bytes per sample group from shared memory instead of 100 global byte loads per butterfly
+        unsigned char *bits_s = reinterpret_cast<unsigned char *>(lut + L::NG * L::ENTRIES);
+        __shared__ __align__(8) unsigned long long bits_bar;
+        const unsigned char *chunk_g = bits + (size_t)item * chunk_bytes;
+        const bool staged = GA_FWD_BULK && (reinterpret_cast<uintptr_t>(chunk_g) & 15) == 0 && (chunk_bytes & 15) == 0 && chunk_bytes <= FWD_BITS_SMEM;
+        if (staged && threadIdx.x == 0) {
+            mbar_init(smem_u32(&bits_bar), 1);
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            mbar_arrive_expect_tx(smem_u32(&bits_bar), (uint32_t)chunk_bytes);
+            bulk_load_1d(smem_u32(bits_s), chunk_g, (uint32_t)chunk_bytes, smem_u32(&bits_bar));
+        }
         for (int e = threadIdx.x; e < L::NG * L::ENTRIES; e += T) lut[e] = fwd_lut_entry<G>(e, k1s);
         __syncthreads();
-        const unsigned char *chunk = bits + (size_t)item * chunk_bytes;
+        if (staged) mbar_wait(smem_u32(&bits_bar), 0);
+        const unsigned char *chunk = staged ? bits_s : chunk_g;
         for (int j = threadIdx.x; j < G::NA; j += T) {
             cf p[G::RA];
 #pragma unroll
@@ -180,8 +233,6 @@ __global__ void __launch_bounds__(T, MODE == 0 ? FWD_MINB : 1) fwd_kernel(const 
 // keep the whole 128-register budget (no local-memory spills, which the register version pays
 // with ~150 M L2 write sectors per launch).
 // ---------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
 template <int N> struct TmVec;   // N 32-bit columns per thread
 template <> struct TmVec<2> {
     static __device__ __forceinline__ void ld(uint32_t a, float *v)

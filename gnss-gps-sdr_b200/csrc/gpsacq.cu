@@ -252,7 +252,7 @@ static int launch_fwd_t(gpsacq *h, size_t n_items, const unsigned char *d_bits, 
 {
     auto kern = fwd_kernel<G, FWD_T, MODE, GID>;
     // opted in once by setup_fwd_t(); MODE 0 carries the sample-group tables behind the tile
-    const int smem = (int)(G::SMEM_ELEMS * sizeof(cf)) + (MODE == 0 && h->d_lomask ? FwdLut<G>::BYTES : 0);
+    const int smem = (int)(G::SMEM_ELEMS * sizeof(cf)) + (MODE == 0 && h->d_lomask ? FwdLut<G>::BYTES + FWD_BITS_SMEM : 0);
     kern<<<(unsigned)(n_items * G::N1), FWD_T, smem, h->stream>>>(d_bits, h->chunk_bytes, h->d_lo, h->d_repl_time,
                                                                   h->d_tw, out, MODE == 0 ? h->d_lomask : nullptr);
     CUDA_TRY(h, cudaGetLastError());
@@ -262,7 +262,7 @@ static int launch_fwd_t(gpsacq *h, size_t n_items, const unsigned char *d_bits, 
 template <class G, int GID> static int setup_fwd_t(gpsacq *h)
 {
     const int smem = (int)(G::SMEM_ELEMS * sizeof(cf));
-    CUDA_TRY(h, cudaFuncSetAttribute(fwd_kernel<G, FWD_T, 0, GID>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem + FwdLut<G>::BYTES));
+    CUDA_TRY(h, cudaFuncSetAttribute(fwd_kernel<G, FWD_T, 0, GID>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem + FwdLut<G>::BYTES + FWD_BITS_SMEM));
     CUDA_TRY(h, cudaFuncSetAttribute(fwd_kernel<G, FWD_T, 1, GID>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     return 0;
 }
