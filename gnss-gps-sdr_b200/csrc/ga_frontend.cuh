@@ -6,6 +6,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include "ga_frontend_math.h"
 
 namespace ga {
 
@@ -75,12 +76,10 @@ __global__ void iq8_to_bits_kernel(const unsigned char *__restrict__ iq, size_t 
     for (int k = 0; k < 8; k++) {
         const size_t n = byte * 8 + k;
         if (n >= n_samples) break;
-        const int a = iq[2 * n], b = iq[2 * n + 1];
-        const double yi = (format == 0 ? a - 128 : (int)(signed char)a) - mean_i;
-        const double yq = (format == 0 ? b - 128 : (int)(signed char)b) - mean_q;
+        const int fx = format == 0 ? 0 : 0x80;                               // int8 -> biased unsigned
         double sn, cs;
         sincos((w * (double)(n0 + n)) * inv_fs, &sn, &cs);
-        const double r = yi * cs - yq * sn;
+        const double r = iq8_r(iq[2 * n] ^ fx, iq[2 * n + 1] ^ fx, mean_i, mean_q, cs, sn);
         out |= (r < 0.0 ? 1u : 0u) << k;                                     // (1-sign(r))/2, LSB first
     }
     bits[byte] = (unsigned char)out;
@@ -123,11 +122,9 @@ __global__ void iq8_to_bits_table_kernel(const unsigned char *__restrict__ iq, s
 #pragma unroll
         for (int j = 0; j < 8; j++) {
             if (byte * 8 + j >= n_samples) break;
-            const int a = raw[2 * j], b = raw[2 * j + 1];
-            const double yi = (format == 0 ? a - 128 : (int)(signed char)a) - mean_i;
-            const double yq = (format == 0 ? b - 128 : (int)(signed char)b) - mean_q;
+            const int fx = format == 0 ? 0 : 0x80;
             const double2 cs = tab[k];
-            const double r = yi * cs.x - yq * cs.y;
+            const double r = iq8_r(raw[2 * j] ^ fx, raw[2 * j + 1] ^ fx, mean_i, mean_q, cs.x, cs.y);
             ob |= (r < 0.0 ? 1u : 0u) << j;
             k += p; if (k >= q) k -= q;
         }
@@ -135,6 +132,56 @@ __global__ void iq8_to_bits_table_kernel(const unsigned char *__restrict__ iq, s
         else bits[byte] = (unsigned char)ob;
     }
     if (whole) reinterpret_cast<unsigned *>(bits)[word] = out;
+}
+
+// pass 2 as a table of thresholds (ga_frontend_math.h): for the usual front-end ratios (fc/fs = p/q, q <= IQ8_THR_MAX_Q)
+// the sign of r for a sample (I, Q, phase k) is  (I - thr[Q][k]) >> 31  -- an exact restatement of the double expression,
+// because the table is MADE by evaluating it for all 256 x 256 x q cases.  No floating point in the hot loop.
+//   iq8_thr_build_kernel   q blocks x 256 threads: entry (Q = thread, k = block) from the integer sums of pass 1 (the mean
+//                          never visits the host: the three kernels of a conversion run back to back on the stream)
+//   iq8_to_bits_thr_kernel persistent CTAs with the table in shared memory; one thread per output byte = 8 samples = one
+//                          128-bit load; the number of working threads is a multiple of q, so the eight phase indices of a
+//                          thread are the same in every trip of its grid-stride loop (kept as eight row offsets in registers);
+//                          per sample: two byte extracts, one multiply-add (row address), one shared load, one subtraction,
+//                          one funnel shift.  Four loads in flight per thread.
+#define IQ8_THR_MAX_Q 227                       // 256 rows x (q | 1) entries x 4 B <= 227 KB of shared memory
+#define IQ8_THR_THREADS 1024
+__global__ void iq8_thr_build_kernel(const long long *__restrict__ sums, size_t n_total, const double2 *__restrict__ tab,
+                                     unsigned pitch, unsigned *__restrict__ thr)
+{
+    const unsigned k = blockIdx.x, qu = threadIdx.x;
+    const double mean_i = (double)sums[0] / (double)n_total, mean_q = (double)sums[1] / (double)n_total;
+    const double2 cs = tab[k];
+    thr[qu * pitch + k] = iq8_thr_entry((int)qu, mean_i, mean_q, cs.x, cs.y);
+}
+
+__global__ void __launch_bounds__(IQ8_THR_THREADS, 1)
+iq8_to_bits_thr_kernel(const uint4 *__restrict__ iq, size_t n_samples, size_t n0, unsigned fx /* 0 or 0x80808080 */,
+                       const unsigned *__restrict__ thr, unsigned p, unsigned q, unsigned pitch, unsigned n_active,
+                       const long long *__restrict__ sums, size_t n_total, const double2 *__restrict__ tab,
+                       unsigned char *__restrict__ bits)
+{
+    extern __shared__ uint4 thr_s4[];
+    {
+        const uint4 *src = reinterpret_cast<const uint4 *>(thr);
+        for (unsigned i = threadIdx.x; i < 64u * pitch; i += blockDim.x) thr_s4[i] = __ldg(src + i);     // 256 * pitch * 4 B
+    }
+    __syncthreads();
+    const tabref_t tab_s = (tabref_t)__cvta_generic_to_shared(thr_s4);
+    const unsigned tid = blockIdx.x * blockDim.x + threadIdx.x, pitch_b = 4u * pitch;
+    const size_t n_bytes = n_samples / 8;
+    if (tid < n_active) iq8_thr_thread(tid, n_active, iq, n_bytes, n0, fx, tab_s, pitch_b, p, q, bits);
+    if (tid == 0 && (n_samples & 7)) {                  // the last n_samples % 8 samples: the double expression itself
+        const double mean_i = (double)sums[0] / (double)n_total, mean_q = (double)sums[1] / (double)n_total;
+        const unsigned char *raw = reinterpret_cast<const unsigned char *>(iq);
+        unsigned ob = 0;
+        for (size_t n = n_bytes * 8; n < n_samples; n++) {
+            const double2 cs = tab[(((n0 + n) % q) * p) % q];
+            const int f = (int)(fx & 0x80u);
+            ob |= (iq8_r(raw[2 * n] ^ f, raw[2 * n + 1] ^ f, mean_i, mean_q, cs.x, cs.y) < 0.0 ? 1u : 0u) << (n & 7);
+        }
+        bits[n_bytes] = (unsigned char)ob;
+    }
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -181,6 +228,17 @@ __global__ void bits_to_iq8_kernel(const unsigned char *__restrict__ bits, size_
         }
         out[byte] = make_uint4(w[0], w[1], w[2], w[3]);
     }
+}
+
+// The same conversion with the per-thread work cut from ~200 to ~40 instructions (the byte-per-sample kernel above is
+// instruction bound: a 64-bit modulo per 16 output bytes and sixteen compare/selects): the position in the LO cycle
+// advances incrementally along the grid-stride loop (32-bit; one 64-bit modulo per THREAD), and the eight samples of a
+// byte are expanded with byte-lane arithmetic and four byte permutes (conv_expand4, ga_frontend_math.h).
+__global__ void bits_to_iq8_v2_kernel(const unsigned char *__restrict__ bits, size_t n_bytes, size_t first_sample,
+                                      const unsigned char *__restrict__ lo, unsigned long long mu, unsigned long long lambda,
+                                      int amp, uint4 *__restrict__ out)
+{
+    conv_v2_thread((size_t)blockIdx.x * blockDim.x + threadIdx.x, (size_t)gridDim.x * blockDim.x, bits, n_bytes, first_sample, lo, mu, lambda, amp, out);
 }
 
 }  // namespace ga

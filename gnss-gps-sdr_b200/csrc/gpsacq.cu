@@ -151,6 +151,7 @@ struct gpsacq {
     int gid, n, n1, n2, w, dmax, ndop, chunk_bytes, chunk_samples, cap, device, sm_count;
     int cell_ctas, cell_threads, cell_smem, cell_nw;
     double *d_iq_tab; unsigned long long iq_tab_p, iq_tab_q; bool iq_tab_neg;     // 8-bit front-end: phasor table of the last shift
+    unsigned *d_iq_thr; bool iq_thr_attr;                                          // ... and its threshold table (ga_frontend_math.h)
     int sub_blocks, last_launch_blocks; // REF: chunks per kernel launch (a batch is cut into launches whose block spectra stay in L2)
     int nseg;                          // REF: output segments of N2 lags per cell (1 unless W > N2, i.e. FS > 10 MHz)
     CellStat *d_cells_seg;
@@ -442,7 +443,7 @@ static void free_all(gpsacq *h)
     if (!h) return;
     cudaFree(h->d_tw); cudaFree(h->d_lo); cudaFree(h->d_lomask); cudaFree(h->d_chip_idx); cudaFree(h->d_blend_a); cudaFree(h->d_blend_b);
     cudaFree(h->d_repl_time); cudaFree(h->d_cext); cudaFree(h->d_xd); cudaFree(h->d_nat); cudaFree(h->d_bits);
-    cudaFree(h->d_crot); cudaFree(h->d_iq_tab); cudaFree(h->d_cells_seg); cudaFree(h->d_sched); cudaFree(h->d_chalo); cudaFree(h->d_sv); cudaFree(h->d_wipe); cudaFree(h->d_xg); cudaFree(h->d_code_w); cudaFree(h->d_cells); cudaFree(h->d_peaks);
+    cudaFree(h->d_crot); cudaFree(h->d_iq_tab); cudaFree(h->d_iq_thr); cudaFree(h->d_cells_seg); cudaFree(h->d_sched); cudaFree(h->d_chalo); cudaFree(h->d_sv); cudaFree(h->d_wipe); cudaFree(h->d_xg); cudaFree(h->d_code_w); cudaFree(h->d_cells); cudaFree(h->d_peaks);
     cudaFreeHost(h->h_bits); cudaFreeHost(h->h_sv); cudaFreeHost(h->h_peaks);
     for (int i = 0; i < 4; i++) if (h->ev[i]) cudaEventDestroy(h->ev[i]);
     for (int i = 0; i < 8; i++) if (h->ev_copy[i]) cudaEventDestroy(h->ev_copy[i]);
@@ -848,8 +849,8 @@ static int acquire_device_impl(gpsacq *h, const uint8_t *d_bits, size_t n_acq, g
     return GPSACQ_OK;
 }
 
-static int iq8_convert_piece(gpsacq *h, const unsigned char *d_iq, size_t n, size_t n0, int format, double mi, double mq,
-                             double shift_hz, double fs, unsigned char *d_bits);
+static int iq8_convert_piece(gpsacq *h, const unsigned char *d_iq, size_t n, size_t n0, int format, const long long *d_sums,
+                             size_t n_total, double shift_hz, double fs, unsigned char *d_bits);
 
 // ---- ABI -------------------------------------------------------------------------------
 extern "C" {
@@ -1065,7 +1066,7 @@ int gpsacq_iq8_to_bits(gpsacq_t *h, const void *iq, size_t n_samples, int format
     const size_t piece = (size_t)1 << 26;                        // complex samples per device buffer (128 MB of IQ)
     const size_t cap = std::min(piece, n_samples);
     unsigned char *d_iq = nullptr, *d_bits = nullptr;
-    long long *d_sums = nullptr, sums[2] = {0, 0};
+    long long *d_sums = nullptr;
     int rc = GPSACQ_OK;
     do {
         if (cudaMalloc(&d_iq, 2 * cap) != cudaSuccess || cudaMalloc(&d_bits, (cap + 7) / 8) != cudaSuccess ||
@@ -1079,16 +1080,13 @@ int gpsacq_iq8_to_bits(gpsacq_t *h, const void *iq, size_t n_samples, int format
             if (n_samples > cap && cudaStreamSynchronize(h->stream) != cudaSuccess) { rc = GPSACQ_ECUDA; break; }
         }
         if (rc) break;
-        if (cudaMemcpyAsync(sums, d_sums, sizeof sums, cudaMemcpyDeviceToHost, h->stream) != cudaSuccess ||
-            cudaStreamSynchronize(h->stream) != cudaSuccess) { rc = GPSACQ_ECUDA; break; }
-        const double mi = (double)sums[0] / (double)n_samples, mq = (double)sums[1] / (double)n_samples;
-        // pass 2: shift, real part, sign, pack
+        // pass 2: shift, real part, sign, pack (the mean = d_sums / n_samples, over the whole capture)
         for (size_t done = 0; done < n_samples; done += cap) {
             const size_t n = std::min(cap, n_samples - done);
             if (n_samples > cap || done > 0)
                 if (cudaMemcpyAsync(d_iq, (const unsigned char *)iq + 2 * done, 2 * n, cudaMemcpyHostToDevice, h->stream) != cudaSuccess) { rc = GPSACQ_ECUDA; break; }
             const size_t nbytes = (n + 7) / 8;
-            if (iq8_convert_piece(h, d_iq, n, done, format, mi, mq, shift_hz, fs, d_bits) != GPSACQ_OK) { rc = GPSACQ_ECUDA; break; }
+            if (iq8_convert_piece(h, d_iq, n, done, format, d_sums, n_samples, shift_hz, fs, d_bits) != GPSACQ_OK) { rc = GPSACQ_ECUDA; break; }
             if (cudaMemcpyAsync(bits_out + done / 8, d_bits, nbytes, cudaMemcpyDeviceToHost, h->stream) != cudaSuccess ||
                 cudaStreamSynchronize(h->stream) != cudaSuccess) { rc = GPSACQ_ECUDA; break; }
         }
@@ -1121,24 +1119,62 @@ static bool small_rational(double x, unsigned long long &p, unsigned long long &
     return false;
 }
 
-static int iq8_convert_piece(gpsacq *h, const unsigned char *d_iq, size_t n, size_t n0, int format, double mi, double mq,
-                             double shift_hz, double fs, unsigned char *d_bits)
+// Stream converters, second version (threshold-table iq8 -> bits, permute-based bits -> iq8; ga_frontend.cuh):
+// GPSACQ_FRONTEND_V2=0/1 overrides the built-in default, for A/B runs.
+#ifndef GA_FRONTEND_V2_DEFAULT
+#define GA_FRONTEND_V2_DEFAULT 0
+#endif
+static bool frontend_v2()
+{
+    const char *e = getenv("GPSACQ_FRONTEND_V2");
+    return (e && *e) ? atoi(e) != 0 : GA_FRONTEND_V2_DEFAULT != 0;
+}
+
+// One piece of pass 2.  d_sums = the integer sums of pass 1 (device), n_total = samples they were taken over.
+static int iq8_convert_piece(gpsacq *h, const unsigned char *d_iq, size_t n, size_t n0, int format, const long long *d_sums,
+                             size_t n_total, double shift_hz, double fs, unsigned char *d_bits)
 {
     const size_t nbytes = (n + 7) / 8;
     unsigned long long p = 0, q = 0;
-    if (small_rational(fabs(shift_hz) / fs, p, q) && ((uintptr_t)d_iq % 16) == 0) {
-        if (h->iq_tab_q != q || h->iq_tab_p != p || h->iq_tab_neg != (shift_hz < 0)) {
-            std::vector<double> tab(2 * q);
-            for (unsigned long long k = 0; k < q; k++) {
-                const long double a = 2.0L * 3.14159265358979323846264338327950288L * (long double)k / (long double)q;
-                tab[2 * k] = (double)cosl(a); tab[2 * k + 1] = (double)(shift_hz < 0 ? -sinl(a) : sinl(a));
-            }
-            CUDA_TRY(h, cudaStreamSynchronize(h->stream));
-            cudaFree(h->d_iq_tab); h->d_iq_tab = nullptr;
-            CUDA_TRY(h, cudaMalloc(&h->d_iq_tab, 2 * q * sizeof(double)));
-            CUDA_TRY(h, cudaMemcpy(h->d_iq_tab, tab.data(), 2 * q * sizeof(double), cudaMemcpyHostToDevice));
-            h->iq_tab_p = p; h->iq_tab_q = q; h->iq_tab_neg = shift_hz < 0;
+    const bool periodic = small_rational(fabs(shift_hz) / fs, p, q) && ((uintptr_t)d_iq % 16) == 0;
+    if (periodic && (h->iq_tab_q != q || h->iq_tab_p != p || h->iq_tab_neg != (shift_hz < 0) || !h->d_iq_tab)) {
+        std::vector<double> tab(2 * q);
+        for (unsigned long long k = 0; k < q; k++) {
+            const long double a = 2.0L * 3.14159265358979323846264338327950288L * (long double)k / (long double)q;
+            tab[2 * k] = (double)cosl(a); tab[2 * k + 1] = (double)(shift_hz < 0 ? -sinl(a) : sinl(a));
         }
+        CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+        cudaFree(h->d_iq_tab); h->d_iq_tab = nullptr;
+        cudaFree(h->d_iq_thr); h->d_iq_thr = nullptr;
+        CUDA_TRY(h, cudaMalloc(&h->d_iq_tab, 2 * q * sizeof(double)));
+        CUDA_TRY(h, cudaMemcpy(h->d_iq_tab, tab.data(), 2 * q * sizeof(double), cudaMemcpyHostToDevice));
+        if (q <= IQ8_THR_MAX_Q) CUDA_TRY(h, cudaMalloc(&h->d_iq_thr, (size_t)256 * iq8_thr_pitch((unsigned)q) * sizeof(unsigned)));
+        h->iq_tab_p = p; h->iq_tab_q = q; h->iq_tab_neg = shift_hz < 0;
+    }
+    if (periodic && q <= IQ8_THR_MAX_Q && (n0 % 8) == 0 && frontend_v2()) {
+        // thresholds from the sums (on the device: no host round trip between the passes), then the integer-only pass 2
+        const unsigned pitch = iq8_thr_pitch((unsigned)q);
+        const size_t smem = (size_t)256 * pitch * sizeof(unsigned);
+        if (!h->iq_thr_attr) {
+            CUDA_TRY(h, cudaFuncSetAttribute(iq8_to_bits_thr_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             256 * (int)iq8_thr_pitch(IQ8_THR_MAX_Q) * (int)sizeof(unsigned)));
+            h->iq_thr_attr = true;
+        }
+        iq8_thr_build_kernel<<<(unsigned)q, 256, 0, h->stream>>>(d_sums, n_total, (const double2 *)h->d_iq_tab, pitch, h->d_iq_thr);
+        CUDA_TRY(h, cudaGetLastError());
+        const unsigned threads = (unsigned)h->sm_count * IQ8_THR_THREADS, n_active = threads / (unsigned)q * (unsigned)q;
+        iq8_to_bits_thr_kernel<<<h->sm_count, IQ8_THR_THREADS, smem, h->stream>>>(
+            (const uint4 *)d_iq, n, n0, format == GPSACQ_IQ_S8 ? 0x80808080u : 0u, h->d_iq_thr, (unsigned)p, (unsigned)q, pitch, n_active,
+            d_sums, n_total, (const double2 *)h->d_iq_tab, d_bits);
+        CUDA_TRY(h, cudaGetLastError());
+        return GPSACQ_OK;
+    }
+    // the double-precision kernels take the mean as an argument
+    long long sums[2];
+    CUDA_TRY(h, cudaMemcpyAsync(sums, d_sums, sizeof sums, cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    const double mi = (double)sums[0] / (double)n_total, mq = (double)sums[1] / (double)n_total;
+    if (periodic) {
         const size_t nwords = (nbytes + 3) / 4;                  // one thread per 32 samples
         const size_t tab_smem = q <= 2048 ? (size_t)q * sizeof(double2) : 0;
         iq8_to_bits_table_kernel<<<(unsigned)((nwords + 255) / 256), 256, tab_smem, h->stream>>>(d_iq, n, n0, format, mi, mq, (const double2 *)h->d_iq_tab, p, q, d_bits);
@@ -1157,14 +1193,10 @@ extern "C" int gpsacq_iq8_to_bits_device(gpsacq_t *h, const void *d_iq, size_t n
         return GPSACQ_EINVAL;
     if (n_samples == 0) return GPSACQ_OK;
     CUDA_TRY(h, cudaSetDevice(h->device));
-    long long sums[2];
     CUDA_TRY(h, cudaMemsetAsync(d_sums, 0, 2 * sizeof(long long), h->stream));
     iq8_sum_kernel<<<h->sm_count * 8, 256, 0, h->stream>>>((const unsigned char *)d_iq, n_samples, format, (long long *)d_sums);
     CUDA_TRY(h, cudaGetLastError());
-    CUDA_TRY(h, cudaMemcpyAsync(sums, d_sums, sizeof sums, cudaMemcpyDeviceToHost, h->stream));
-    CUDA_TRY(h, cudaStreamSynchronize(h->stream));               // the mean is a kernel argument of pass 2
-    return iq8_convert_piece(h, (const unsigned char *)d_iq, n_samples, 0, format, (double)sums[0] / (double)n_samples,
-                             (double)sums[1] / (double)n_samples, shift_hz, fs, d_bits_out);
+    return iq8_convert_piece(h, (const unsigned char *)d_iq, n_samples, 0, format, (const long long *)d_sums, n_samples, shift_hz, fs, d_bits_out);
 }
 
 // ---- the reverse converter: 1-bit real IF -> int8 IQ (c/conv_1bit_bin_to_hackrf_bin.cpp:29-86) -------------------------
@@ -1237,7 +1269,10 @@ extern "C" int gpsacq_bits_to_iq8_device(int device, const uint8_t *d_bits, size
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     const size_t want = (n_bytes + 255) / 256;
     const unsigned grid = (unsigned)std::min<size_t>(want, (size_t)sms * 16);
-    bits_to_iq8_kernel<<<grid, 256, 0, (cudaStream_t)cuda_stream>>>(d_bits, n_bytes, first_sample, g_conv.d_lo, g_conv.cyc.mu, g_conv.cyc.lambda, amplitude, (uint4 *)d_iq_out);
+    if (frontend_v2())
+        bits_to_iq8_v2_kernel<<<grid, 256, 0, (cudaStream_t)cuda_stream>>>(d_bits, n_bytes, first_sample, g_conv.d_lo, g_conv.cyc.mu, g_conv.cyc.lambda, amplitude, (uint4 *)d_iq_out);
+    else
+        bits_to_iq8_kernel<<<grid, 256, 0, (cudaStream_t)cuda_stream>>>(d_bits, n_bytes, first_sample, g_conv.d_lo, g_conv.cyc.mu, g_conv.cyc.lambda, amplitude, (uint4 *)d_iq_out);
     if (cudaGetLastError() != cudaSuccess) { g_create_error = "bits_to_iq8: kernel launch failed"; return GPSACQ_ECUDA; }
     return GPSACQ_OK;
 }

@@ -11,6 +11,7 @@
 #include "ga_fft3.h"
 #include "ga_tables.h"
 #include "ga_pfa.h"
+#include "ga_frontend_math.h"
 
 using namespace ga;
 
@@ -296,6 +297,61 @@ int emu_fwd(int id, const float *x, int s, float *out)
     case 4: emu_fwd_t<X4096>((const cf *)x, s, (cf *)out); return 0;
     }
     return -1;
+}
+
+// ---- stream converters (csrc/ga_frontend.cuh): the kernels' thread functions, every thread in a loop ----------------
+// iq8 -> bits through the threshold table (iq8_thr_build_kernel + iq8_to_bits_thr_kernel); n_threads = threads of the launch
+int emu_iq8_thr(const unsigned char *iq, size_t n_samples, size_t n0, int fmt_s8, long long sum_i, long long sum_q, size_t n_total,
+                const double *tab, unsigned p, unsigned q, unsigned n_threads, unsigned char *bits)
+{
+    const unsigned pitch = iq8_thr_pitch(q), n_active = n_threads / q * q, fx = fmt_s8 ? 0x80808080u : 0u;
+    if (!n_active) return -1;
+    const double mean_i = (double)sum_i / (double)n_total, mean_q = (double)sum_q / (double)n_total;
+    std::vector<unsigned> thr((size_t)256 * pitch);
+    for (unsigned k = 0; k < q; k++)                       // iq8_thr_build_kernel: block k, thread qu
+        for (unsigned qu = 0; qu < 256; qu++) thr[(size_t)qu * pitch + k] = iq8_thr_entry((int)qu, mean_i, mean_q, tab[2 * k], tab[2 * k + 1]);
+    const size_t n_bytes = n_samples / 8;
+    std::vector<u32x4> in(n_bytes + 1);
+    memcpy(in.data(), iq, 16 * n_bytes);
+    for (unsigned tid = 0; tid < n_active; tid++)
+        iq8_thr_thread(tid, n_active, in.data(), n_bytes, n0, fx, (tabref_t)thr.data(), 4u * pitch, p, q, bits);
+    if (n_samples & 7) {
+        unsigned ob = 0;
+        for (size_t n = n_bytes * 8; n < n_samples; n++) {
+            const size_t k = (((n0 + n) % q) * p) % q;
+            const int f = (int)(fx & 0x80u);
+            ob |= (iq8_r(iq[2 * n] ^ f, iq[2 * n + 1] ^ f, mean_i, mean_q, tab[2 * k], tab[2 * k + 1]) < 0.0 ? 1u : 0u) << (n & 7);
+        }
+        bits[n_bytes] = (unsigned char)ob;
+    }
+    return 0;
+}
+
+// the same decision sample by sample from the double expression (what iq8_to_bits_table_kernel evaluates)
+int emu_iq8_direct(const unsigned char *iq, size_t n_samples, size_t n0, int fmt_s8, long long sum_i, long long sum_q, size_t n_total,
+                   const double *tab, unsigned p, unsigned q, unsigned char *bits)
+{
+    const double mean_i = (double)sum_i / (double)n_total, mean_q = (double)sum_q / (double)n_total;
+    const int f = fmt_s8 ? 0x80 : 0;
+    memset(bits, 0, (n_samples + 7) / 8);
+    for (size_t n = 0; n < n_samples; n++) {
+        const size_t k = (((n0 + n) % q) * p) % q;
+        if (iq8_r(iq[2 * n] ^ f, iq[2 * n + 1] ^ f, mean_i, mean_q, tab[2 * k], tab[2 * k + 1]) < 0.0) bits[n / 8] |= (unsigned char)(1u << (n & 7));
+    }
+    return 0;
+}
+
+// bits -> iq8, second version (bits_to_iq8_v2_kernel); lo: mu + lambda codes followed by 16 zero bytes
+int emu_conv_v2(const unsigned char *bits, size_t n_bytes, size_t first_sample, const unsigned char *lo, unsigned long long mu,
+                unsigned long long lambda, int amp, size_t n_threads, unsigned char *out)
+{
+    std::vector<u32x4> o(n_bytes + 1);
+    std::vector<unsigned> lo_al((size_t)(mu + lambda + 16 + 3) / 4);          // 4-byte aligned like the cudaMalloc'ed table
+    memcpy(lo_al.data(), lo, (size_t)(mu + lambda + 16));
+    for (size_t tid = 0; tid < n_threads; tid++)
+        conv_v2_thread(tid, n_threads, bits, n_bytes, first_sample, (const unsigned char *)lo_al.data(), mu, lambda, amp, o.data());
+    memcpy(out, o.data(), 16 * n_bytes);
+    return 0;
 }
 
 }

@@ -8,6 +8,15 @@ import pytest
 pytestmark = pytest.mark.gpu
 
 
+@pytest.fixture(autouse=True, params=[0, 1], ids=["v1", "v2"])
+def frontend_version(request, monkeypatch):
+    """Every test of this file runs through both kernel generations of the converters: the double-precision table kernel /
+    compare-select expander, and the threshold-table / byte-permute kernels (csrc/ga_frontend.cuh; the library reads
+    GPSACQ_FRONTEND_V2 on every call)."""
+    monkeypatch.setenv("GPSACQ_FRONTEND_V2", str(request.param))
+    return request.param
+
+
 def matlab_restatement(iq_u8: np.ndarray, fc: float, fs: float, signed: bool) -> np.ndarray:
     """proc_rtl_bin_for_gps.m:31-47 (uint8) / proc_hackrf_bin_for_gps.m:7-19 (int8), line by line, in double."""
     y = iq_u8.view(np.int8).astype(np.float64) if signed else iq_u8.astype(np.float64) - 128      # :34  y = y - 128
@@ -56,6 +65,27 @@ def test_iq8_frontend_edges(ga):
         assert out.size == 2 and out[1] < 32
     finally:
         acq.close()
+
+
+@pytest.mark.parametrize("fc,fs,signed,n", [(0.62e6, 2.8e6, False, 40960 * 24 + 5), (2.6e6, 10e6, True, 1_000_003),
+                                            (4.092e6, 5.456e6, False, 123_457), (0.0, 2.8e6, True, 65_536)])
+def test_iq8_threshold_kernel_equals_double_kernel(ga, monkeypatch, fc, fs, signed, n):
+    """Threshold-table pass 2 == the double-precision pass 2, bit for bit (the table is made by evaluating the same
+    expression; tests/test_frontend_emu.py shows it on the CPU), including samples hugging the mean and the tail."""
+    rng = np.random.default_rng(n)
+    iq = rng.integers(0, 256, 2 * n, dtype=np.uint8)
+    iq[: 2 * 50_000] = np.clip(rng.normal(128, 2.5, 2 * 50_000), 0, 255).astype(np.uint8)
+    acq = ga.Acquisition(0.62e6, 2.8e6)
+    try:
+        monkeypatch.setenv("GPSACQ_FRONTEND_V2", "0")
+        a = acq.iq8_to_bits(iq, fc, fs, signed=signed)
+        monkeypatch.setenv("GPSACQ_FRONTEND_V2", "1")
+        b = acq.iq8_to_bits(iq, fc, fs, signed=signed)
+        c = acq.iq8_to_bits(iq, -fc, fs, signed=signed)          # the other shift direction rebuilds both tables
+    finally:
+        acq.close()
+    assert a.size == (n + 7) // 8 and np.array_equal(a, b)
+    assert a.any() and (fc == 0.0 or not np.array_equal(b, c))
 
 
 # ---- the reverse converter: 1-bit IF -> int8 IQ (c/conv_1bit_bin_to_hackrf_bin.cpp:29-86), pinned by the reference program ----

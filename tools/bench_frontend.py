@@ -35,15 +35,20 @@ def timed(fn, reps=5):
     return e0.elapsed_time(e1) / reps
 
 
-ms = timed(lambda: acq.iq8_to_bits_device(iq.data_ptr(), n, 0.62e6, 2.8e6, bits.data_ptr(), sums.data_ptr()))
-moved = 2 * (2 * n) + n // 8                   # two reads of the IQ bytes + the packed bits
-print(json.dumps({"converter": "iq8_to_bits", "samples": n, "ms": ms, "gsamples_per_s": n / ms / 1e6,
-                  "gbs_moved": moved / ms / 1e6, "frac_of_hbm_peak": moved / ms / 1e6 / peak,
-                  "note": "2 B read twice (exact integer mean, then shift + sign) + 1/8 B written per sample"}))
-out = torch.zeros(2 * n, dtype=torch.int8, device=dev)
-ms = timed(lambda: ga.bits_to_iq8_device(bits.data_ptr(), n // 8, 2.6e6, 10e6, out.data_ptr(), device=0, stream_ptr=stream.cuda_stream))
-moved = n // 8 + 2 * n
-print(json.dumps({"converter": "bits_to_iq8", "samples": n, "ms": ms, "gsamples_per_s": n / ms / 1e6,
-                  "gbs_moved": moved / ms / 1e6, "frac_of_hbm_peak": moved / ms / 1e6 / peak,
-                  "note": "1/8 B read + 2 B written per sample"}))
+import os
+for version in (1, 2):          # 1: double-precision table kernel / compare-select expander; 2: threshold table / byte permutes
+    os.environ["GPSACQ_FRONTEND_V2"] = "1" if version == 2 else "0"
+    ms = timed(lambda: acq.iq8_to_bits_device(iq.data_ptr(), n, 0.62e6, 2.8e6, bits.data_ptr(), sums.data_ptr()))
+    moved = 2 * (2 * n) + n // 8                   # two reads of the IQ bytes + the packed bits
+    print(json.dumps({"converter": "iq8_to_bits", "version": version, "samples": n, "ms": ms, "gsamples_per_s": n / ms / 1e6,
+                      "gbs_moved": moved / ms / 1e6, "frac_of_hbm_peak": moved / ms / 1e6 / peak,
+                      "note": "2 B read twice (exact integer mean, then shift + sign) + 1/8 B written per sample"}), flush=True)
+    out = torch.zeros(2 * n, dtype=torch.int8, device=dev)
+    ms = timed(lambda: ga.bits_to_iq8_device(bits.data_ptr(), n // 8, 2.6e6, 10e6, out.data_ptr(), device=0, stream_ptr=stream.cuda_stream))
+    moved = n // 8 + 2 * n
+    print(json.dumps({"converter": "bits_to_iq8", "version": version, "samples": n, "ms": ms, "gsamples_per_s": n / ms / 1e6,
+                      "gbs_moved": moved / ms / 1e6, "frac_of_hbm_peak": moved / ms / 1e6 / peak,
+                      "note": "1/8 B read + 2 B written per sample"}), flush=True)
+    del out
+del os.environ["GPSACQ_FRONTEND_V2"]
 acq.close()
