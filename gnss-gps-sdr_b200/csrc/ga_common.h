@@ -40,6 +40,14 @@ GA_HD cf mk(float x, float y) { cf r; r.x = x; r.y = y; return r; }
 #define GA_PACKED 1
 GA_HD cf cadd(cf a, cf b) { return __fadd2_rn(a, b); }
 GA_HD cf csub(cf a, cf b) { return __fadd2_rn(a, mk(-b.x, -b.y)); }
+// The same sums as two scalar FADDs (identical bits; __fadd_rn is never contracted).  A packed instruction holds the
+// FMA-heavy pipe for two cycles and a scalar FADD issues beside it for free (tools/ubench/fp32x2.cu on a B200:
+// FFMA2 2.1 cycles per warp-instruction per sub-partition, FFMA2 + FADD 1:1 1.04 -- profiles/r02_fp32x2.txt), at the
+// price of a second issue slot: the butterflies pick per call site (GA_R4_SCALAR, GA_R5_SCALAR).
+GA_HD cf cadd_s(cf a, cf b) { return mk(__fadd_rn(a.x, b.x), __fadd_rn(a.y, b.y)); }
+GA_HD cf csub_s(cf a, cf b) { return mk(__fadd_rn(a.x, -b.x), __fadd_rn(a.y, -b.y)); }
+template <int DIR> GA_HD cf cadd_i_s(cf a, cf b) { return DIR > 0 ? mk(__fadd_rn(a.x, -b.y), __fadd_rn(a.y, b.x)) : mk(__fadd_rn(a.x, b.y), __fadd_rn(a.y, -b.x)); }
+template <int DIR> GA_HD cf csub_i_s(cf a, cf b) { return DIR > 0 ? mk(__fadd_rn(a.x, b.y), __fadd_rn(a.y, -b.x)) : mk(__fadd_rn(a.x, -b.y), __fadd_rn(a.y, b.x)); }
 GA_HD cf cmul(cf a, cf b) { return __ffma2_rn(mk(a.y, a.x), mk(-b.y, b.y), __fmul2_rn(a, mk(b.x, b.x))); }
 GA_HD cf csqr(cf a) { return cmul(a, a); }
 GA_HD cf cscale(cf a, float s) { return __fmul2_rn(a, mk(s, s)); }
@@ -54,12 +62,16 @@ GA_HD void cfma(cf &acc, cf a, cf b) { acc = __ffma2_rn(mk(a.y, a.x), mk(-b.y, b
 #define GA_PACKED 0
 GA_HD cf cadd(cf a, cf b) { return mk(a.x + b.x, a.y + b.y); }
 GA_HD cf csub(cf a, cf b) { return mk(a.x - b.x, a.y - b.y); }
+GA_HD cf cadd_s(cf a, cf b) { return cadd(a, b); }
+GA_HD cf csub_s(cf a, cf b) { return csub(a, b); }
 GA_HD cf cmul(cf a, cf b) { return mk(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x); }
 GA_HD cf csqr(cf a) { return mk(a.x * a.x - a.y * a.y, 2.0f * a.x * a.y); }
 GA_HD cf cscale(cf a, float s) { return mk(a.x * s, a.y * s); }
 GA_HD cf caxpy(cf acc, cf a, float s) { return mk(fmaf(a.x, s, acc.x), fmaf(a.y, s, acc.y)); }
 template <int DIR> GA_HD cf cadd_i(cf a, cf b) { return DIR > 0 ? mk(a.x - b.y, a.y + b.x) : mk(a.x + b.y, a.y - b.x); }
 template <int DIR> GA_HD cf csub_i(cf a, cf b) { return DIR > 0 ? mk(a.x + b.y, a.y - b.x) : mk(a.x - b.y, a.y + b.x); }
+template <int DIR> GA_HD cf cadd_i_s(cf a, cf b) { return cadd_i<DIR>(a, b); }
+template <int DIR> GA_HD cf csub_i_s(cf a, cf b) { return csub_i<DIR>(a, b); }
 GA_HD void cfma(cf &acc, cf a, cf b)
 {
     acc.x = fmaf(a.x, b.x, acc.x); acc.x = fmaf(-a.y, b.y, acc.x);

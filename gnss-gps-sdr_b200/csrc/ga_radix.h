@@ -45,6 +45,19 @@ template <int I, int NITER, class F> GA_HD void static_for(F &&f)
 }
 
 // ---- primitives --------------------------------------------------------------
+#ifndef GA_R4_SCALAR
+#define GA_R4_SCALAR 0
+#endif
+#ifndef GA_R5_SCALAR
+#define GA_R5_SCALAR 0
+#endif
+// Scalar FADD pairs instead of FADD2 (ga_common.h: same bits, FMA-lite pipe, one more issue slot), per call site, measured on
+// a B200 with byte-identical peak records (tools/gpu_r2y.sh, gpu_r2z.sh, gpu_r2zz.sh; profiles/r02_scalar_adds.txt):
+//   prime radices (GRID kernels, FMA pipe 71 % busy): input and output sums scalar  +0.9 ... +2.2 %  -> default
+//   radix 4 (inside 16 / 20 / 24): REF +0.3 %, GRID -1 %;   radix 5 (inside 20 / 25): REF -0.2 ... -0.4 %   -> packed
+#ifndef GA_RP_SCALAR        // prime radices: bit 0 = the input sums / differences scalar, bit 1 = the output sums
+#define GA_RP_SCALAR 3
+#endif
 template <int R, int DIR> struct Radix;
 
 template <int DIR> struct Radix<1, DIR> { static GA_HD void run(cf (&)[1]) {} };
@@ -60,13 +73,11 @@ template <int DIR> struct Radix<2, DIR> {
 template <int DIR> struct Radix<4, DIR> {
     static GA_HD void run(cf (&x)[4])
     {
-#if defined(GA_R4_SCALAR) && GA_PACKED
-        // experiment: scalar adds (can issue on the fmalite pipe) instead of FADD2 (fmaheavy only)
-        const cf s0 = mk(x[0].x + x[2].x, x[0].y + x[2].y), d0 = mk(x[0].x - x[2].x, x[0].y - x[2].y);
-        const cf s1 = mk(x[1].x + x[3].x, x[1].y + x[3].y), d1 = mk(x[1].x - x[3].x, x[1].y - x[3].y);
-        x[0] = mk(s0.x + s1.x, s0.y + s1.y); x[2] = mk(s0.x - s1.x, s0.y - s1.y);
-        if (DIR > 0) { x[1] = mk(d0.x - d1.y, d0.y + d1.x); x[3] = mk(d0.x + d1.y, d0.y - d1.x); }
-        else         { x[1] = mk(d0.x + d1.y, d0.y - d1.x); x[3] = mk(d0.x - d1.y, d0.y + d1.x); }
+#if GA_R4_SCALAR        // scalar adds (FMA-lite pipe, beside the packed instructions) instead of FADD2
+        const cf s0 = cadd_s(x[0], x[2]), d0 = csub_s(x[0], x[2]);
+        const cf s1 = cadd_s(x[1], x[3]), d1 = csub_s(x[1], x[3]);
+        x[0] = cadd_s(s0, s1); x[1] = cadd_i_s<DIR>(d0, d1);
+        x[2] = csub_s(s0, s1); x[3] = csub_i_s<DIR>(d0, d1);
 #else
         const cf s0 = cadd(x[0], x[2]), d0 = csub(x[0], x[2]);
         const cf s1 = cadd(x[1], x[3]), d1 = csub(x[1], x[3]);
@@ -81,15 +92,26 @@ template <int DIR> struct Radix<5, DIR> {
     {
         constexpr float c1 = (float)cx_cos2pi(1, 5), c2 = (float)cx_cos2pi(2, 5);
         constexpr float s1 = (float)cx_sin2pi(1, 5), s2 = (float)cx_sin2pi(2, 5);
+#if GA_R5_SCALAR == 1  // the input sums / differences scalar
+        const cf t1 = cadd_s(x[1], x[4]), t3 = csub_s(x[1], x[4]);
+        const cf t2 = cadd_s(x[2], x[3]), t4 = csub_s(x[2], x[3]);
+#else
         const cf t1 = cadd(x[1], x[4]), t3 = csub(x[1], x[4]);
         const cf t2 = cadd(x[2], x[3]), t4 = csub(x[2], x[3]);
+#endif
         const cf b1 = caxpy(caxpy(x[0], t1, c1), t2, c2);
         const cf b2 = caxpy(caxpy(x[0], t1, c2), t2, c1);
         const cf d1 = caxpy(cscale(t3, s1), t4, s2);         // X1 = b1 + DIR*i*d1
         const cf d2 = caxpy(cscale(t3, s2), t4, -s1);
+#if GA_R5_SCALAR == 2  // the output sums scalar
+        x[0] = cadd_s(x[0], cadd_s(t1, t2));
+        x[1] = cadd_i_s<DIR>(b1, d1); x[4] = csub_i_s<DIR>(b1, d1);
+        x[2] = cadd_i_s<DIR>(b2, d2); x[3] = csub_i_s<DIR>(b2, d2);
+#else
         x[0] = cadd(x[0], cadd(t1, t2));
         x[1] = cadd_i<DIR>(b1, d1); x[4] = csub_i<DIR>(b1, d1);
         x[2] = cadd_i<DIR>(b2, d2); x[3] = csub_i<DIR>(b2, d2);
+#endif
     }
 };
 
@@ -172,7 +194,10 @@ template <int P, int DIR> struct RadixPrime {
     {
         cf s[H], d[H];
         GA_UNROLL
-        for (int k = 1; k <= H; k++) { s[k - 1] = cadd(x[k], x[P - k]); d[k - 1] = csub(x[k], x[P - k]); }
+        for (int k = 1; k <= H; k++) {
+            if (GA_RP_SCALAR & 1) { s[k - 1] = cadd_s(x[k], x[P - k]); d[k - 1] = csub_s(x[k], x[P - k]); }
+            else { s[k - 1] = cadd(x[k], x[P - k]); d[k - 1] = csub(x[k], x[P - k]); }
+        }
         const cf x0 = x[0];
         {   // X_0: pairwise tree
             cf t[H];
@@ -194,8 +219,13 @@ template <int P, int DIR> struct RadixPrime {
                 a = caxpy(a, s[k - 1], c);
                 b = (k == 1) ? cscale(d[0], sn) : caxpy(b, d[k - 1], sn);
             });
-            emit(std::integral_constant<int, j>{}, cadd_i<DIR>(a, b));          // a + DIR*i*b
-            emit(std::integral_constant<int, P - j>{}, csub_i<DIR>(a, b));
+            if (GA_RP_SCALAR & 2) {
+                emit(std::integral_constant<int, j>{}, cadd_i_s<DIR>(a, b));
+                emit(std::integral_constant<int, P - j>{}, csub_i_s<DIR>(a, b));
+            } else {
+                emit(std::integral_constant<int, j>{}, cadd_i<DIR>(a, b));      // a + DIR*i*b
+                emit(std::integral_constant<int, P - j>{}, csub_i<DIR>(a, b));
+            }
         });
     }
     static GA_HD void run(cf (&x)[P])

@@ -1122,7 +1122,7 @@ static bool small_rational(double x, unsigned long long &p, unsigned long long &
 // Stream converters, second version (threshold-table iq8 -> bits, permute-based bits -> iq8; ga_frontend.cuh):
 // GPSACQ_FRONTEND_V2=0/1 overrides the built-in default, for A/B runs.
 #ifndef GA_FRONTEND_V2_DEFAULT
-#define GA_FRONTEND_V2_DEFAULT 0
+#define GA_FRONTEND_V2_DEFAULT 1
 #endif
 static bool frontend_v2()
 {

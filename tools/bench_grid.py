@@ -49,6 +49,6 @@ for name in (sys.argv[1:] or list(CONFIGS)):
                       "cells_per_s": corr / c["K"] / ms * 1e3, "acquisitions_per_s": n_acq / ms * 1e3,
                       "stage_ms": {k: round(v, 3) for k, v in st.items()},
                       "bytes_per_corr": bpc, "contract_gbs": corr * bpc / ms / 1e6, "frac_of_hbm_peak": corr * bpc / ms / 1e6 / peak,
-                      "detected": int((pk["snr"] >= 25).sum()), "fft_len_embedded": acq.info["fft_len"],
+                      "detected": int((pk["snr"] >= 25).sum()), "peaks_sha256": __import__("hashlib").sha256(pk.tobytes()).hexdigest()[:16], "fft_len_embedded": acq.info["fft_len"],
                       "cell_threads": acq.info["cell_threads"], "cell_ctas": acq.info["cell_ctas"]}))
     acq.close()
