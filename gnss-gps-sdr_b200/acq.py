@@ -240,7 +240,8 @@ class Acquisition:
 
     def iq8_to_bits_device(self, d_iq_ptr: int, n_samples: int, shift_hz: float, fs: float, d_bits_ptr: int, d_sums_ptr: int,
                            signed: bool = False):
-        """Device-buffer form of iq8_to_bits (asynchronous on the handle's stream apart from the read-back of the mean)."""
+        """Device-buffer form of iq8_to_bits, asynchronous on the handle's stream (ratios shift_hz/fs that are not a small
+        fraction p/q, q <= 227, read the mean back once inside the call)."""
         self._check(self._lib.gpsacq_iq8_to_bits_device(self._h, d_iq_ptr, n_samples, 1 if signed else 0, shift_hz, fs,
                                                         d_bits_ptr, d_sums_ptr))
 

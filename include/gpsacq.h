@@ -193,7 +193,10 @@ int  gpsacq_iq8_to_bits(gpsacq_t *h, const void *iq, size_t n_samples, int forma
                         double fs, uint8_t *bits_out);
 
 /* The same front-end with device-resident buffers, asynchronous on the handle's stream (d_iq: 2*n_samples bytes,
- * d_bits_out: ceil(n_samples/8) bytes, d_sums: 16 bytes of scratch).  For captures that fit in device memory. */
+ * d_bits_out: ceil(n_samples/8) bytes, d_sums: 16 bytes of scratch).  For captures that fit in device memory.
+ * When shift_hz/fs is a fraction p/q with q <= 227 (0.62/2.8, 2.6/10, n/4 ...) and d_iq is 16-byte aligned, the three
+ * kernels (mean, threshold table, conversion) run back to back without a host round trip; other ratios read the mean
+ * back (one stream synchronisation inside the call).  The bits are the same either way. */
 int  gpsacq_iq8_to_bits_device(gpsacq_t *h, const void *d_iq, size_t n_samples, int format, double shift_hz,
                                double fs, uint8_t *d_bits_out, void *d_sums);
 
