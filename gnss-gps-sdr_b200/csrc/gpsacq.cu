@@ -13,6 +13,7 @@
 #include <vector>
 #include <string>
 #include <algorithm>
+#include <mutex>
 
 #include "../../include/gpsacq.h"
 
@@ -1239,6 +1240,7 @@ static bool conv_lo_cycle(double fc, double fs, unsigned long long n_needed, LoC
 
 struct ConvState { int device; double fc, fs; unsigned char *d_lo; LoCycle cyc; };
 static ConvState g_conv = {-1, 0, 0, nullptr, {}};
+static std::mutex g_conv_mutex;        // the cached LO table is process-wide: table (re)build + launch are one critical section
 
 static int conv_prepare(int device, double fc, double fs, unsigned long long n_needed)
 {
@@ -1263,6 +1265,7 @@ extern "C" int gpsacq_bits_to_iq8_device(int device, const uint8_t *d_bits, size
     if (device >= 0 && cudaSetDevice(device) != cudaSuccess) { g_create_error = "bits_to_iq8: cudaSetDevice failed (no CPU fallback)"; return GPSACQ_ECUDA; }
     int dev = 0;
     if (cudaGetDevice(&dev) != cudaSuccess) { g_create_error = "bits_to_iq8: no CUDA device (no CPU fallback)"; return GPSACQ_ECUDA; }
+    std::lock_guard<std::mutex> lock(g_conv_mutex);
     const int rc = conv_prepare(dev, fc, fs, first_sample + 8ull * n_bytes);
     if (rc) return rc;
     int sms = 148;
