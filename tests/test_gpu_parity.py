@@ -134,6 +134,24 @@ def test_gps_test_binary_vs_golden_stdout(name):
     compare_runs(got_runs, ref_runs[: c["runs"]])
 
 
+@pytest.mark.parametrize("which", ["fc", "max_fo"])
+def test_cxx_host_rereads_the_globals_like_the_reference(tmp_path, which):
+    """FC / max_fo changed between SearchInit() and SearchTask() (tests/host/host_globals.cpp): the reference reads them in
+    Sample() / Correlate() only (c/search_offline.cpp:127,176), so its output is the golden stdout of the constant-globals
+    run; the C++ host here has to notice the change and rebuild its engine."""
+    c = CAPTURES["nottingham"]
+    exe = tmp_path / "host_globals"
+    subprocess.run(["g++", "-O1", "-std=c++17", f"-I{PKG / 'c'}", str(ROOT / "tests/host/host_globals.cpp"),
+                    str(PKG / "c/search_offline.cpp"), "-o", str(exe), f"-L{PKG / 'csrc'}", "-lgpsacq",
+                    f"-Wl,-rpath,{PKG / 'csrc'}", "-lpthread"], check=True)
+    r = subprocess.run([str(exe), str(c["bin"]), which], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout + r.stderr
+    got_runs, tail = parse_stdout(r.stdout)
+    ref_runs, _ = parse_stdout(strip_banner(c["stdout"].read_text()))
+    assert tail == ["run out of file!"] and len(got_runs) == c["runs"]
+    compare_runs(got_runs, ref_runs[: c["runs"]])
+
+
 # ---- the whole bundled capture (north_star acceptance; README.md:61, c/search_offline.cpp:219-292) ----------
 FULL_CAPTURE = ROOT / "oracle" / "_ref" / "data" / "gps.samples.1bit.I.fs5456.if4092.bin"      # staged by `make -C oracle`
 FULL_PEAKS = GOLD / "ref_peaks_nottingham_full.npy"          # the reference's Sample()+Correlate() on all 10,880 chunks
