@@ -160,3 +160,42 @@ def test_conv_v2_vs_oracle_restatement(emu, oracle_mod, fc, fs):
     out = np.zeros(16 * bits.size, np.uint8)
     assert emu.emu_conv_v2(p8(bits), bits.size, 0, p8(lo), 0, n, 30, 777, p8(out)) == 0
     assert np.array_equal(out.view(np.int8), want)
+
+
+# ---- randomised sweeps (hypothesis): shapes the hand-picked cases above do not name --------------------------------
+from hypothesis import given, settings, strategies as st
+from math import gcd
+
+
+@settings(max_examples=60, deadline=None)
+@given(q=st.integers(1, 227), pnum=st.integers(0, 226), signed=st.booleans(), n=st.integers(1, 3000), blk=st.integers(0, 1 << 20),
+       threads=st.sampled_from([32, 96, 1024, 5000]), spread=st.sampled_from([1.5, 20.0, 200.0]), seed=st.integers(0, 2 ** 31))
+def test_threshold_table_equals_the_double_expression_random(emu, q, pnum, signed, n, blk, threads, spread, seed):
+    p = pnum % q
+    g = gcd(p, q) if p else q
+    p, q = (p // g, q // g) if p else (0, 1)                 # lowest terms, like small_rational()
+    if threads < q:
+        threads = q
+    rng = np.random.default_rng(seed)
+    iq = np.clip(rng.normal(128 + rng.uniform(-3, 3), spread, 2 * n), 0, 255).astype(np.uint8)
+    si, sq = sums_of(iq, signed)
+    tab = phasor_table(p, q, neg=bool(seed & 1))
+    a = np.zeros((n + 7) // 8, np.uint8)
+    b = np.zeros_like(a)
+    dp = tab.ctypes.data_as(C.POINTER(C.c_double))
+    assert emu.emu_iq8_thr(p8(iq), n, 8 * blk, int(signed), si, sq, n, dp, p, q, threads, p8(a)) == 0
+    assert emu.emu_iq8_direct(p8(iq), n, 8 * blk, int(signed), si, sq, n, dp, p, q, p8(b)) == 0
+    assert np.array_equal(a, b)
+
+
+@settings(max_examples=60, deadline=None)
+@given(mu=st.integers(0, 300), lam=st.integers(1, 5000), first=st.integers(0, 100000), nbytes=st.integers(1, 1500),
+       threads=st.sampled_from([1, 7, 32, 256, 4096]), amp=st.integers(0, 127), seed=st.integers(0, 2 ** 31))
+def test_conv_v2_thread_function_random(emu, mu, lam, first, nbytes, threads, amp, seed):
+    rng = np.random.default_rng(seed)
+    lo = np.zeros(mu + lam + 16, np.uint8)
+    lo[: mu + lam] = rng.integers(0, 4, mu + lam, dtype=np.uint8)
+    bits = rng.integers(0, 256, nbytes, dtype=np.uint8)
+    out = np.zeros(16 * nbytes, np.uint8)
+    assert emu.emu_conv_v2(p8(bits), nbytes, first, p8(lo), mu, lam, amp, threads, p8(out)) == 0
+    assert np.array_equal(out.view(np.int8), conv_plain(bits, first, lo, mu, lam, amp))
