@@ -12,6 +12,7 @@
 #include "ga_tables.h"
 #include "ga_pfa.h"
 #include "ga_frontend_math.h"
+#include "ga_frontend_host.h"
 
 using namespace ga;
 
@@ -352,6 +353,34 @@ int emu_conv_v2(const unsigned char *bits, size_t n_bytes, size_t first_sample, 
         conv_v2_thread(tid, n_threads, bits, n_bytes, first_sample, (const unsigned char *)lo_al.data(), mu, lambda, amp, o.data());
     memcpy(out, o.data(), 16 * n_bytes);
     return 0;
+}
+
+// ---- host-side table preparation of the converters (csrc/ga_frontend_host.h) ---------------------------------------------
+int emu_small_rational(double x, unsigned long long *p, unsigned long long *q) { return small_rational(x, *p, *q) ? 1 : 0; }
+
+// conv_lo_cycle's table applied to samples first .. first + n - 1 (k = i below mu, else mu + (i - mu) mod lambda), next to the
+// float recurrence of c/conv_1bit_bin_to_hackrf_bin.cpp:33,79-80 run sample by sample from 0 (`direct`); returns 0 when the
+// cycle search gives up
+int emu_conv_lo_cycle(double fc, double fs, unsigned long long first, unsigned long long n, unsigned long long *mu,
+                      unsigned long long *lambda, unsigned char *via_table, unsigned char *direct)
+{
+    LoCycle c;
+    if (!conv_lo_cycle(fc, fs, first + n, c)) return 0;
+    *mu = c.mu; *lambda = c.lambda;
+    static const int lo_sin[4] = {1, 1, 0, 0}, lo_cos[4] = {1, 0, 0, 1};
+    const float rate = (float)(4 * fc / fs);
+    float ph = 0;
+    for (unsigned long long i = 0; i < first + n; i++) {
+        if (i >= first) {
+            const unsigned long long k = i < c.mu ? i : c.mu + (i - c.mu) % c.lambda;
+            via_table[i - first] = c.tab[k];
+            const int ip = (int)ph;
+            direct[i - first] = (unsigned char)(lo_sin[ip] | (lo_cos[ip] << 1));
+        }
+        ph += rate;
+        if (ph >= 4) ph -= 4;
+    }
+    return 1;
 }
 
 }

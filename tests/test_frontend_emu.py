@@ -199,3 +199,49 @@ def test_conv_v2_thread_function_random(emu, mu, lam, first, nbytes, threads, am
     out = np.zeros(16 * nbytes, np.uint8)
     assert emu.emu_conv_v2(p8(bits), nbytes, first, p8(lo), mu, lam, amp, threads, p8(out)) == 0
     assert np.array_equal(out.view(np.int8), conv_plain(bits, first, lo, mu, lam, amp))
+
+
+# ---- host-side table preparation (csrc/ga_frontend_host.h) ----------------------------------------------------------------
+@pytest.mark.parametrize("num,den,want", [(0.62e6, 2.8e6, (31, 140)), (2.6e6, 10e6, (13, 50)), (4.092e6, 5.456e6, (3, 4)),
+                                          (2.046e6, 8.184e6, (1, 4)), (0.0, 2.8e6, (0, 1)), (1e6 / 3, 2.8e6, (5, 42)),
+                                          (3.5e6, 2.8e6, (1, 4)), (4.1304e6, 16.368e6, (1721, 6820))])
+def test_small_rational(emu, num, den, want):
+    """shift_hz / fs as a fraction in lowest terms, reduced modulo one turn (p < q)."""
+    from fractions import Fraction
+    p, q = C.c_ulonglong(), C.c_ulonglong()
+    emu.emu_small_rational.argtypes = [C.c_double, C.POINTER(C.c_ulonglong), C.POINTER(C.c_ulonglong)]
+    assert emu.emu_small_rational(num / den, C.byref(p), C.byref(q)) == 1
+    assert (p.value, q.value) == want
+    f = Fraction(num / den).limit_denominator(1 << 20)
+    assert (f.numerator % f.denominator, f.denominator) == want
+
+
+def test_small_rational_rejects_what_is_not_one(emu):
+    p, q = C.c_ulonglong(), C.c_ulonglong()
+    emu.emu_small_rational.argtypes = [C.c_double, C.POINTER(C.c_ulonglong), C.POINTER(C.c_ulonglong)]
+    for x in (np.pi / 10, 123456.789 / 2.8e6, float("nan"), -0.25, 1e7):
+        assert emu.emu_small_rational(x, C.byref(p), C.byref(q)) == 0
+
+
+@pytest.mark.parametrize("fc,fs,first,n", [(4.092e6, 5.456e6, 0, 100_000), (2.046e6, 8.184e6, 12_345, 100_000),
+                                           (2.6e6, 10e6, 0, 3_000_000), (2.6e6, 10e6, 9_000_000, 1_000_000),
+                                           (0.62e6, 2.8e6, 0, 2_000_000), (4.1304e6, 16.368e6, 5_000_001, 1_000_000)])
+def test_conv_lo_cycle_table_is_the_float_recurrence(emu, fc, fs, first, n):
+    """Brent's cycle search + (pre-period, period) table == the float phase NCO of :33,:79-80 run sample by sample, also
+    far beyond one period; the sample-by-sample loop itself is pinned to numpy float32 arithmetic on its first samples."""
+    emu.emu_conv_lo_cycle.argtypes = [C.c_double, C.c_double, C.c_ulonglong, C.c_ulonglong, C.POINTER(C.c_ulonglong),
+                                      C.POINTER(C.c_ulonglong), U8P, U8P]
+    mu, lam = C.c_ulonglong(), C.c_ulonglong()
+    a, b = np.zeros(n, np.uint8), np.zeros(n, np.uint8)
+    assert emu.emu_conv_lo_cycle(fc, fs, first, n, C.byref(mu), C.byref(lam), p8(a), p8(b)) == 1
+    assert np.array_equal(a, b)
+    assert lam.value >= 1 and mu.value + lam.value <= (1 << 28)
+    if first == 0:
+        rate, ph = np.float32(4 * fc / fs), np.float32(0)
+        lo_sin, lo_cos = [1, 1, 0, 0], [1, 0, 0, 1]
+        for i in range(20_000):
+            k = int(ph)
+            assert b[i] == lo_sin[k] | (lo_cos[k] << 1)
+            ph = np.float32(ph + rate)
+            if ph >= 4:
+                ph = np.float32(ph - np.float32(4))

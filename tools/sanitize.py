@@ -52,7 +52,7 @@ with ga.Acquisition(4.092e6, 5.456e6, max_blocks=32) as a:
     for v in ("0", "1"):
         os.environ["GPSACQ_FRONTEND_V2"] = v
         b1 = a.iq8_to_bits(iq[: 2 * 49997], 2.6e6, 10e6, signed=True)
-        b2 = a.iq8_to_bits(iq[: 2 * 1234], 1.0e6 / 3.0, 2.8e6)          # not a small fraction: the sincos kernel
+        b2 = a.iq8_to_bits(iq[: 2 * 1234], 123456.789, 2.8e6)          # not a small fraction: the sincos kernel
         out = ga.bits_to_iq8(data[: 4099], 2.6e6, 10e6, 30, first_sample=8 * 777)
         print("converters v" + v, int(b1[:4].sum()), int(b2[:4].sum()), int(out[:8].astype(int).sum()))
     del os.environ["GPSACQ_FRONTEND_V2"]
