@@ -149,6 +149,37 @@ def test_live_reference_agrees_with_oracle(oracle_mod):
     subprocess.run([sys.executable, "-c", code], check=True)
 
 
+@pytest.mark.parametrize("fs,fc,max_fo", [(2.8e6, 0.62e6, 5000.0),        # rtl-sdr rate: inexact float LO step, 143 bins, 10 x 4000 geometry
+                                          (10e6, 2.6e6, 5000.0),           # the receiver's own rate (c/gps.h:23-24)
+                                          (16.368e6, 4.1304e6, 5000.0),    # W = 16368 > 10000: two output segments on the GPU
+                                          (4e6, 1e6, 5000.0),
+                                          (5.456e6, 4.092e6, 2000.0),      # another max_fo: dmax = (int)(max_fo*N/FS) (:176)
+                                          (8.184e6, 2.046e6, 12345.6),
+                                          (8e6, 2e6, 5000.0), (16.368e6, 4.092e6, 5000.0), (25e6, 6.25e6, 5000.0), (40e6, 10e6, 5000.0)])
+def test_live_reference_agrees_with_oracle_at_other_rates(oracle_mod, ga, fs, fc, max_fo):
+    """The GPU tests at these rates (test_synthetic_vs_oracle, test_high_sampling_rates_vs_oracle,
+    test_max_fo_changes_the_doppler_grid) compare the engine with the C restatement; here the restatement is pinned to the
+    UNMODIFIED reference TU at the same rates: synthetic capture, eight chunks searched for the satellites that are in it.
+    (One reference instance per process: it keeps its state in file statics.)"""
+    if not oracle_mod.ref_available():
+        pytest.skip("oracle/_ref/libref_harness.so not built (needs /root/reference)")
+    code = (
+        "import sys, importlib; sys.path.insert(0, %r); sys.path.insert(0, %r); import numpy as np, oracle, gpsacq_loader\n"
+        "gpsacq_loader.load(); sg = importlib.import_module('gnss_gps_sdr_b200.siggen')\n"
+        "fs, fc, max_fo = %r, %r, %r\n"
+        "sats = sg.default_constellation(fs, cn0_dbhz=48.0 if fs <= 10e6 else 57.0, seed=11, max_doppler=0.9 * min(max_fo, 4500.0))\n"
+        "d = sg.synth_capture(8 * 40960, fs, fc, sats, seed=5).tobytes()\n"
+        "sv = np.array([s['prn'] - 1 for s in sats], np.int32)\n"
+        "r = oracle.RefHarness(fc, fs, max_fo); o = oracle.Oracle(fc, fs, max_fo)\n"
+        "a = r.search_blocks(d, sv); b = o.search_blocks(d, sv)\n"
+        "assert (a['snr'] >= 25).sum() >= 6, a['snr']\n"
+        "assert np.array_equal(a['lo_shift'], b['lo_shift']) and np.array_equal(a['ca_shift'], b['ca_shift'])\n"
+        "assert np.abs(a['snr'] / b['snr'] - 1).max() < 1e-5\n"
+        "for s_, p in zip(sats, a): assert p['snr'] < 25 or abs(p['lo_shift'] - s_['doppler_hz'] * 40000 / fs) <= 1.0\n"
+    ) % (str(ROOT / "oracle"), str(ROOT), fs, fc, max_fo)
+    subprocess.run([sys.executable, "-c", code], check=True, env=oracle_mod.mkl_env())
+
+
 # ---- GRID mode: the C oracle against an independent numpy restatement of the definition (SURVEY App. E) -------
 @pytest.mark.parametrize("fs,fc,step,K", [(2.8e6, 0.62e6, 250.0, 2), (5.456e6, 4.092e6, 500.0, 1)])
 def test_grid_oracle_matches_numpy_definition(oracle_mod, ga, fs, fc, step, K):
