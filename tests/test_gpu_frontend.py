@@ -18,7 +18,9 @@ def frontend_version(request, monkeypatch):
 
 
 def matlab_restatement(iq_u8: np.ndarray, fc: float, fs: float, signed: bool) -> np.ndarray:
-    """proc_rtl_bin_for_gps.m:31-47 (uint8) / proc_hackrf_bin_for_gps.m:7-19 (int8), line by line, in double."""
+    """proc_rtl_bin_for_gps.m:31-47 (uint8) / proc_hackrf_bin_for_gps.m:7-19 (int8), line by line, in double.
+    PARITY UNPINNED: neither MATLAB nor Octave is available and the reference bundles no output of these scripts, so this
+    restatement is checked against nothing but its source text."""
     y = iq_u8.view(np.int8).astype(np.float64) if signed else iq_u8.astype(np.float64) - 128      # :34  y = y - 128
     y = y[0::2] + 1j * y[1::2]                                                                     # :35
     y = y - y.mean()                                                                               # :36
