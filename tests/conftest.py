@@ -159,3 +159,23 @@ def replay_target(g, bits, feed_chunk, signal_lost):
         for e in lost_after.get(c, []):
             signal_lost(e["ch"], e["sv"])
     return got
+
+
+# ---- the unmodified reference's peaks at sampling rates without a bundled capture (tests/golden/ref_peaks_rates.npz, made
+# by tests/golden/make_golden_rates.py from synthetic captures that are regenerated, not stored) -------------------------
+def rates_golden(name: str, bits: np.ndarray) -> np.ndarray:
+    """Reference records of case `name`; `bits` = the regenerated input, checked against the SHA-256 recorded with the golden."""
+    import hashlib
+    import json
+    meta = json.loads((GOLD / "ref_peaks_rates.json").read_text())
+    assert hashlib.sha256(np.ascontiguousarray(bits).tobytes()).hexdigest() == meta["inputs"][name]["sha256"], \
+        f"the numpy generator no longer reproduces the input of golden case {name}"
+    return np.load(GOLD / "ref_peaks_rates.npz")[name]
+
+
+def rates_case(fs: float, fc: float, seed: int) -> str:
+    import json
+    for name, c in json.loads((GOLD / "ref_peaks_rates.json").read_text())["cases"].items():
+        if (c["fs"], c["fc"], c["seed"]) == (fs, fc, seed):
+            return name
+    raise KeyError((fs, fc, seed))

@@ -7,7 +7,8 @@ import subprocess
 import numpy as np
 import pytest
 
-from conftest import CAPTURES, GOLD, ROOT, SNR_RTOL, compare_peaks, compare_runs, parse_stdout, strip_banner
+from conftest import (CAPTURES, GOLD, ROOT, SNR_RTOL, compare_peaks, compare_runs, parse_stdout, rates_case, rates_golden,
+                      strip_banner)
 
 pytestmark = pytest.mark.gpu
 PKG = ROOT / "gnss-gps-sdr_b200"
@@ -274,6 +275,7 @@ def test_high_sampling_rates_vs_oracle(engines, oracle_mod, siggen, fs, fc, seed
     W = int(np.ceil(fs / 1000))
     assert acq.info["window"] == W and acq.info["n2"] == 10000 and acq.n_doppler == 2 * int(5000.0 * 40000 / fs) + 1
     got = acq.search_blocks(bits)
+    compare_peaks(got, rates_golden(rates_case(fs, fc, seed), bits))       # what the UNMODIFIED reference returned for this input
     o = oracle_mod.Oracle(fc, fs)
     ref = o.search_blocks(bits)
     compare_peaks(got, ref)
@@ -287,7 +289,8 @@ def test_high_sampling_rates_vs_oracle(engines, oracle_mod, siggen, fs, fc, seed
         assert np.array_equal(acq.replica_time(sv).view(np.uint32), oracle_mod.replica_time(fs, sv).view(np.uint32))
 
 
-# ---- other sampling rates, synthetic captures (no reference fixture exists) --------------------------------
+# ---- other sampling rates, synthetic captures: the reference bundles no capture at these rates, so its records for
+# these synthetic inputs were taken by running it unmodified (tests/golden/make_golden_rates.py) ---------------------
 # (8 MHz and 4 MHz exercise the wide-window variants of the 8000- and 4000-point geometries: 20 / 10 accumulators per
 # butterfly, 448-thread and 128-thread CTA shapes)
 @pytest.mark.parametrize("fs,fc,seed", [(2.8e6, 0.62e6, 1575420001), (10e6, 2.6e6, 3), (5.456e6, 4.092e6, 1575420000),
@@ -297,6 +300,8 @@ def test_synthetic_vs_oracle(engines, oracle_mod, siggen, fs, fc, seed):
     bits = siggen.synth_capture(40960 * 32, fs, fc, sats, seed=seed)
     acq = engines(fc, fs)
     got = acq.search_blocks(bits)
+    # the unmodified reference's records for this very input (tests/golden/ref_peaks_rates.npz), then the C restatement
+    compare_peaks(got, rates_golden(rates_case(fs, fc, seed), bits))
     ref = oracle_mod.Oracle(fc, fs).search_blocks(bits)
     compare_peaks(got, ref)
     for s in sats:                      # every generated satellite is found at its Doppler bin
