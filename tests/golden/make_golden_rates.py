@@ -31,6 +31,9 @@ CASES = {
     "hi_16368": dict(fs=16.368e6, fc=4.092e6, max_fo=5000.0, seed=13, cn0=57.0, chunks=32),
     "hi_25000": dict(fs=25e6, fc=6.25e6, max_fo=5000.0, seed=14, cn0=57.0, chunks=32),
     "hi_40000": dict(fs=40e6, fc=10e6, max_fo=5000.0, seed=15, cn0=57.0, chunks=32),
+    # test_max_fo_changes_the_doppler_grid: one satellite outside the default +-5 kHz span, searched with max_fo = 10 kHz
+    "maxfo_10000": dict(fs=5.456e6, fc=4.092e6, max_fo=10000.0, seed=5, cn0=None, chunks=9,
+                        sats=[dict(prn=9, doppler_hz=7300.0, code_phase_chips=100.25, amp=0.3)]),
 }
 
 
@@ -39,7 +42,7 @@ def case_bits(name: str) -> np.ndarray:
     gpsacq_loader.load()
     sg = importlib.import_module("gnss_gps_sdr_b200.siggen")
     c = CASES[name]
-    sats = sg.default_constellation(c["fs"], cn0_dbhz=c["cn0"], seed=c["seed"])
+    sats = c.get("sats") or sg.default_constellation(c["fs"], cn0_dbhz=c["cn0"], seed=c["seed"])
     return sg.synth_capture(40960 * c["chunks"], c["fs"], c["fc"], sats, seed=c["seed"])
 
 

@@ -316,6 +316,7 @@ def test_max_fo_changes_the_doppler_grid(engines, oracle_mod, siggen):
     acq = engines(fc, fs, 10000.0)
     assert acq.n_doppler == 2 * int(10000.0 * 40000 / fs) + 1
     got = acq.search_blocks(bits)
+    compare_peaks(got, rates_golden("maxfo_10000", bits))          # the unmodified reference with max_fo = 10000 on this input
     ref = oracle_mod.Oracle(fc, fs, 10000.0).search_blocks(bits)
     compare_peaks(got, ref)
     assert got[8]["lo_shift"] == round(7300.0 * 40000 / fs)

@@ -180,7 +180,8 @@ def test_live_reference_agrees_with_oracle_at_other_rates(oracle_mod, ga, fs, fc
     subprocess.run([sys.executable, "-c", code], check=True, env=oracle_mod.mkl_env())
 
 
-@pytest.mark.parametrize("name", ["syn_2800", "syn_10000", "syn_5456", "syn_8000", "syn_4000", "hi_16368", "hi_25000", "hi_40000"])
+@pytest.mark.parametrize("name", ["syn_2800", "syn_10000", "syn_5456", "syn_8000", "syn_4000", "hi_16368", "hi_25000", "hi_40000",
+                                  "maxfo_10000"])
 def test_oracle_matches_reference_goldens_at_other_rates(oracle_mod, ga, name):
     """tests/golden/ref_peaks_rates.npz holds what the UNMODIFIED reference returned for the synthetic captures the GPU tests
     search at 2.8 ... 40 MHz (32 chunks each, all 32 PRNs): the C restatement reproduces it -- integers, and SNR far inside
@@ -190,7 +191,7 @@ def test_oracle_matches_reference_goldens_at_other_rates(oracle_mod, ga, name):
     from conftest import GOLD, compare_peaks, rates_golden
     sg = importlib.import_module("gnss_gps_sdr_b200.siggen")
     c = json.loads((GOLD / "ref_peaks_rates.json").read_text())["cases"][name]
-    sats = sg.default_constellation(c["fs"], cn0_dbhz=c["cn0"], seed=c["seed"])
+    sats = c.get("sats") or sg.default_constellation(c["fs"], cn0_dbhz=c["cn0"], seed=c["seed"])
     bits = sg.synth_capture(40960 * c["chunks"], c["fs"], c["fc"], sats, seed=c["seed"])
     ref = rates_golden(name, bits)
     got = oracle_mod.Oracle(c["fc"], c["fs"], c["max_fo"]).search_blocks(bits.tobytes())
