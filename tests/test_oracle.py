@@ -260,6 +260,30 @@ def test_grid_oracle_agrees_with_the_reference_on_the_capture(oracle_mod):
         assert min(d, 5456 - d) <= 1 and abs(p["lo_shift"] * 500.0 - ref[i]["lo_shift"] * c["fs"] / 40000) <= 500.0
 
 
+def test_grid_definition_equals_the_reference_where_the_two_coincide(oracle_mod, ga):
+    """At FS = 40 MHz the reference's 40000-sample window IS one 1 ms block, and with doppler_step = FS/N = 1 kHz its
+    spectrum rotation by whole bins IS the time-domain wipe-off of the GRID definition: GRID mode (SURVEY App. E -- new
+    semantics) and Correlate() then describe the same computation.  The GRID oracle run that way reproduces the UNMODIFIED
+    reference's records for the 40 MHz golden input (tests/golden/ref_peaks_rates.npz, case hi_40000): every Doppler bin and
+    code phase, SNR to 1e-6 -- mixer, LO restart, replica NCO, wipe-off sign, conjugate on the data, statistics and the
+    best-over-Doppler scan of the definition are thereby pinned to the reference itself."""
+    import importlib
+    import json
+    from conftest import GOLD, rates_golden
+    sg = importlib.import_module("gnss_gps_sdr_b200.siggen")
+    c = json.loads((GOLD / "ref_peaks_rates.json").read_text())["cases"]["hi_40000"]
+    sats = sg.default_constellation(c["fs"], cn0_dbhz=c["cn0"], seed=c["seed"])
+    bits = sg.synth_capture(40960 * c["chunks"], c["fs"], c["fc"], sats, seed=c["seed"])
+    ref = rates_golden("hi_40000", bits)
+    g = oracle_mod.GridOracle(c["fc"], c["fs"], c["max_fo"], c["fs"] / 40000.0, 1)
+    assert g.window == 40000 and g.n_doppler == 2 * int(c["max_fo"] * 40000 / c["fs"]) + 1
+    chunks = bits.reshape(c["chunks"], 5120)
+    got = np.concatenate([g.acquire(chunks[b, :5000], svs=[b % 32]) for b in range(c["chunks"])])   # samples 40000.. are discarded there too
+    assert (ref["snr"] >= 25).sum() >= 6
+    assert np.array_equal(got["lo_shift"], ref["lo_shift"]) and np.array_equal(got["ca_shift"], ref["ca_shift"])
+    assert np.abs(got["snr"].astype(np.float64) / ref["snr"] - 1).max() < 1e-6
+
+
 def test_grid_oracle_vs_the_dataset_page_known_answer(oracle_mod):
     """250 Hz bins on the first 20 ms of the capture: PRN 1/21/29/30/31 within +-1 bin of lo_shift 6/8/-9/-9/-8
     ("Raw GPS signal samples data set for testing GPS receivers.html", Holme's search on this file)."""
