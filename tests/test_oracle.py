@@ -282,6 +282,19 @@ def test_grid_definition_equals_the_reference_where_the_two_coincide(oracle_mod,
     assert (ref["snr"] >= 25).sum() >= 6
     assert np.array_equal(got["lo_shift"], ref["lo_shift"]) and np.array_equal(got["ca_shift"], ref["ca_shift"])
     assert np.abs(got["snr"].astype(np.float64) / ref["snr"] - 1).max() < 1e-6
+    # a 500 Hz grid (wipe-off period M = FS/step = 80000 != W): its EVEN bins are the reference's bins; the reference's
+    # scan (ascending, strictly greater, :173,:198) over the per-bin statistics of those bins gives the same records
+    g2 = oracle_mod.GridOracle(c["fc"], c["fs"], c["max_fo"], c["fs"] / 80000.0, 1)
+    assert g2.n_doppler == 2 * g.n_doppler - 1
+    for b in range(0, c["chunks"], 3):
+        _, cells = g2.acquire(chunks[b, :5000], want_cells=True, svs=[b % 32])
+        cm, ci, ct = cells[0]
+        best = (np.float32(0), 0, 0)
+        for di in range(0, g2.n_doppler, 2):
+            snr = np.float32(cm[0, di]) / (np.float32(ct[0, di]) / np.float32(g2.window))
+            if snr > best[0]:
+                best = (snr, (di - g2.dmax) // 2, int(ci[0, di]))
+        assert (best[1], best[2]) == (ref["lo_shift"][b], ref["ca_shift"][b]) and abs(float(best[0]) / float(ref["snr"][b]) - 1) < 1e-6
 
 
 def test_grid_oracle_vs_the_dataset_page_known_answer(oracle_mod):
