@@ -291,3 +291,35 @@ def test_pfa_kernel_math_replay_matches_numpy(W):
                        ctypes.byref(best), ctypes.byref(bi), ctypes.byref(sm), ctypes.byref(slow))
         assert bi.value == want and slow.value > 0
         assert best.value == fill and sm.value == fill * W
+
+
+# ---- argument validation happens before any device is touched: checkable without a GPU ---------------------------------
+def test_argument_validation_precedes_the_device(ga):
+    """Bad configurations are GPSACQ_EINVAL (-1) with a message -- never GPSACQ_ECUDA (-2), which is what a VALID configuration
+    gets on a box without a GPU.  REF: FS / fft_len / max_fo limits of c/search_offline.cpp:176,190 and c/gps_offline.h:15;
+    GRID: block-length and grid rules of SURVEY App. E; stream converters and generator: argument checks."""
+    import ctypes as C
+    bad = [dict(fc=4e6, fs=-1.0), dict(fc=4e6, fs=0.0), dict(fc=-1.0, fs=5.456e6), dict(fc=4e6, fs=40.5e6),     # FS/1000 > FFT_LEN
+           dict(fc=4e6, fs=5.456e6, max_fo=-5.0), dict(fc=4e6, fs=5.456e6, max_fo=2e6),                         # dmax >= N2
+           dict(fc=4e6, fs=float("nan")), dict(fc=4e6, fs=5.456e6, mode=7),
+           dict(fc=4e6, fs=5.456e6, mode=1, doppler_step=0.0), dict(fc=4e6, fs=5.4561e6, mode=1, doppler_step=500.0),   # W not a multiple of 8
+           dict(fc=4e6, fs=5.456e6, mode=1, doppler_step=333.0),                                                       # FS/step not an integer
+           dict(fc=4e6, fs=16.368e6, mode=1, doppler_step=500.0),                                                      # GRID: W > 10000
+           dict(fc=4e6, fs=5.456e6, mode=1, doppler_step=500.0, dop_first=20, dop_count=5)]                           # shard outside the grid
+    for kw in bad:
+        with pytest.raises(ga.GpsAcqError, match=r"failed \(-1\)"):
+            ga.Acquisition(**kw)
+    lib = ga.load_library()
+    assert lib.gpsacq_create(None, None) == -1
+    # converters / generator: bad arguments are rejected before the device is selected
+    out = (C.c_ubyte * 64)()
+    assert lib.gpsacq_bits_to_iq8(0, None, C.c_size_t(8), C.c_size_t(0), C.c_double(2.6e6), C.c_double(10e6), 30, out) == -1
+    lib.gpsacq_bits_to_iq8_device.argtypes = [C.c_int, C.c_void_p, C.c_size_t, C.c_size_t, C.c_double, C.c_double, C.c_int, C.c_void_p, C.c_void_p]
+    assert lib.gpsacq_bits_to_iq8_device(0, C.c_void_p(16), 8, 0, 2.6e6, 10e6, 200, C.c_void_p(16), None) == -1      # amplitude > 127
+    assert lib.gpsacq_bits_to_iq8(0, out, C.c_size_t(0), C.c_size_t(0), C.c_double(2.6e6), C.c_double(10e6), 30, out) == 0     # empty input: nothing to do
+    with pytest.raises(ga.GpsAcqError):
+        ga.synth_capture_gpu(4096, 5.456e6, 4.092e6, [dict(prn=40, doppler_hz=0.0, code_phase_chips=0.0, amp=1.0)])
+    with pytest.raises(ga.GpsAcqError):
+        ga.synth_capture_gpu(4096, 5.456e6, 4.092e6, [dict(prn=3, doppler_hz=0.0, code_phase_chips=-2.0, amp=1.0)])
+    with pytest.raises(ga.GpsAcqError):
+        ga.sig_gen_literal(0, np.zeros(4, np.uint8))
